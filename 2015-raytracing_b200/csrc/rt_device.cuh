@@ -1,0 +1,458 @@
+// rt_device.cuh -- device-side building blocks of the B200 ray tracer.
+//
+// Every function here computes exactly what one helper of the reference's OpenCL kernels
+// computes, in the same fp32 operation order (file:line cited per function, paths relative
+// to /root/reference; A10 = Assign10-Path_Tracing).  The translation unit is compiled with
+// -fmad=false (no contraction; the one explicit `mad` of the reference is an explicit
+// fmaf), IEEE division and square root (nvcc defaults -prec-div=true -prec-sqrt=true,
+// -ftz=false), so results are bit-comparable with the reference text evaluated under the
+// evaluation order documented in DESIGN.md ("arithmetic contract").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rt {
+
+// ---------------------------------------------------------------------------------------
+// Memory layouts (reference: A10/code.cl:22-62)
+// ---------------------------------------------------------------------------------------
+struct __align__(16) Ray {   // 48 B
+    float ox, oy, oz, _p0;
+    float dx, dy, dz, _p1;
+    float mint, maxt, _p2, _p3;
+};
+struct __align__(16) Poi10 { // 64 B (A10)
+    float px, py, pz, _p0;
+    float nx, ny, nz, _p1;
+    float ax, ay, az, _p2;   // atte
+    int matId, _p3, _p4, _p5;
+};
+struct __align__(16) Poi8 {  // 48 B (A08/A09)
+    float px, py, pz, _p0;
+    float nx, ny, nz, _p1;
+    int matId, _p2, _p3, _p4;
+};
+static_assert(sizeof(Ray) == 48 && sizeof(Poi10) == 64 && sizeof(Poi8) == 48, "reference layouts");
+
+struct f3 { float x, y, z; };
+struct f2 { float x, y; };
+struct AABB { f3 pmin, pmax; };
+struct Camera {           // A10/code.cl:33-38, floatToCamera :73-84
+    f3 eye, U, V, W;
+    float width, height;
+    unsigned cols, rows;
+};
+
+#define RT_DEV __device__ __forceinline__
+#define RT_INF __int_as_float(0x7f800000)
+
+RT_DEV f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+RT_DEV f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_DEV f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_DEV f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_DEV f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+RT_DEV f3 operator*(float s, f3 a) { return mk3(s * a.x, s * a.y, s * a.z); }
+RT_DEV f3 operator/(f3 a, float s) { return mk3(a.x / s, a.y / s, a.z / s); }
+RT_DEV f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+RT_DEV float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RT_DEV f3 cross(f3 a, f3 b) { return mk3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+RT_DEV float length(f3 a) { return sqrtf(dot(a, a)); }
+RT_DEV float distance(f3 a, f3 b) { return length(a - b); }
+RT_DEV f3 normalize(f3 a) { return a / length(a); }
+// OpenCL min/max on floats as the C ternaries of the spec (NaN behaviour differs from fminf).
+RT_DEV float cl_min(float x, float y) { return y < x ? y : x; }
+RT_DEV float cl_max(float x, float y) { return x < y ? y : x; }
+RT_DEV float cl_clamp(float x, float lo, float hi) { return cl_min(cl_max(x, lo), hi); }
+RT_DEV float cl_cos(float a) { return (float)cos((double)a); }
+RT_DEV float cl_sin(float a) { return (float)sin((double)a); }
+
+RT_DEV Camera floatToCamera(const float* in) {   // A10/code.cl:73-84
+    Camera c;
+    c.eye = mk3(in[0], in[1], in[2]);
+    c.U = mk3(in[3], in[4], in[5]);
+    c.V = mk3(in[6], in[7], in[8]);
+    c.W = mk3(in[9], in[10], in[11]);
+    c.width = in[12];
+    c.height = in[13];
+    c.cols = (unsigned)in[14];
+    c.rows = (unsigned)in[15];
+    return c;
+}
+
+struct CamArg { float v[16]; };    // by-value float16 kernel argument
+struct AabbArg { float v[8]; };    // by-value AABB (pmin.xyzw, pmax.xyzw)
+struct LightArg { float v[16]; };  // by-value float16 light packing (A10/code.js:323-352)
+
+RT_DEV AABB toAABB(const AabbArg& a) {
+    AABB b;
+    b.pmin = mk3(a.v[0], a.v[1], a.v[2]);
+    b.pmax = mk3(a.v[4], a.v[5], a.v[6]);
+    return b;
+}
+
+// ---------------------------------------------------------------------------------------
+// Ray load/store helpers (vectorised: 3 x 16 B)
+// ---------------------------------------------------------------------------------------
+struct RayR {   // register form
+    f3 o, d;
+    float mint, maxt;
+};
+RT_DEV RayR loadRay(const Ray* p) {
+    const float4* q = reinterpret_cast<const float4*>(p);
+    float4 a = q[0], b = q[1], c = q[2];
+    RayR r;
+    r.o = mk3(a.x, a.y, a.z);
+    r.d = mk3(b.x, b.y, b.z);
+    r.mint = c.x;
+    r.maxt = c.y;
+    return r;
+}
+RT_DEV void storeRay(Ray* p, const RayR& r) {
+    float4* q = reinterpret_cast<float4*>(p);
+    q[0] = make_float4(r.o.x, r.o.y, r.o.z, 0.0f);
+    q[1] = make_float4(r.d.x, r.d.y, r.d.z, 0.0f);
+    q[2] = make_float4(r.mint, r.maxt, 0.0f, 0.0f);
+}
+RT_DEV void storeDeadRay(Ray* p) {   // "ray.mint = ray.maxt = HUGE_VALF" with the rest unspecified
+    float4* q = reinterpret_cast<float4*>(p);
+    q[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    q[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    q[2] = make_float4(RT_INF, RT_INF, 0.0f, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------
+// Camera rays
+// ---------------------------------------------------------------------------------------
+RT_DEV f3 getPoint(f3 o, f3 d, float t) { return o + t * d; }   // A10/code.cl:86-88
+
+// A10/code.cl:108-119.  col,row arrive as float (uint -> float at the call site).
+RT_DEV void getRay(const Camera& cam, float col, float row, f3& o, f3& d) {
+    f3 cop = (-0.5f + (col + 0.5f) / (float)cam.cols) * cam.width * cam.U +
+             (0.5f - (row + 0.5f) / (float)cam.rows) * cam.height * cam.V +
+             (-1.0f) * cam.W;
+    d = normalize(cop);
+    o = cam.eye;
+}
+
+// A10/code.cl:143-172 (Shirley/Whittle concentric map).
+RT_DEV f2 concentric_distort(f2 in) {
+    if (in.x == 0.0f && in.y == 0.0f) return in;
+    float phi = 0.0f;
+    float radius = 1.0f;
+    float a = (2.0f * in.x) - 1.0f;
+    float b = (2.0f * in.y) - 1.0f;
+    if ((a * a) > (b * b)) {
+        radius *= a;
+        phi = 0.78539816339744830962f * (b / a);
+    } else {
+        radius *= b;
+        phi = 1.57079632679489661923f - (0.78539816339744830962f * (a / b));
+    }
+    f2 r;
+    r.x = cl_cos(phi) * radius;
+    r.y = cl_sin(phi) * radius;
+    return r;
+}
+
+// A10/code.cl:174-181.
+RT_DEV f3 getFocalPoint(const Camera& cam, float col, float row, float focal_length) {
+    f3 o, d;
+    getRay(cam, col, row, o, d);
+    f3 pip = cam.eye + focal_length * cam.W * (-1.0f);
+    f3 N = cam.W;
+    float dd = -dot(pip, N);
+    float t = -(dot(o, N) + dd) / dot(d, N);
+    return getPoint(o, d, t);
+}
+
+// A10/code.cl:183-197.
+RT_DEV void getThinLensRay(const Camera& cam, f3 focal_point, float lens_rad, f2 coord, f3& o, f3& d) {
+    f2 dc = concentric_distort(coord);
+    dc.x = dc.x * lens_rad;
+    dc.y = dc.y * lens_rad;
+    o = cam.eye + dc.x * cam.U + dc.y * cam.V;
+    d = normalize(focal_point - o);
+}
+
+// A10/code.cl:121-129.
+RT_DEV RayR makeRay(f3 ori, f3 dst) {
+    RayR r;
+    r.o = ori;
+    r.d = normalize(dst - ori);
+    r.mint = 0.0f;
+    r.maxt = length(dst - ori);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------
+// Intersections
+// ---------------------------------------------------------------------------------------
+struct AabbHit { float tmin, tmax; bool v; };
+
+// A10/code.cl:335-389.  Starts from [0,+inf) and ignores ray.mint/maxt.
+RT_DEV AabbHit interAABB(f3 o, f3 d, const AABB& box) {
+    AabbHit h;
+    h.tmin = 0.0f;
+    h.tmax = RT_INF;
+    h.v = false;
+    float ttmin, ttmax, tmp;
+    ttmin = (box.pmin.x - o.x) / d.x;
+    ttmax = (box.pmax.x - o.x) / d.x;
+    if (d.x < 0) { tmp = ttmin; ttmin = ttmax; ttmax = tmp; }
+    h.tmin = cl_max(ttmin, h.tmin);
+    h.tmax = cl_min(ttmax, h.tmax);
+    if (h.tmin > h.tmax) return h;
+    ttmin = (box.pmin.y - o.y) / d.y;
+    ttmax = (box.pmax.y - o.y) / d.y;
+    if (d.y < 0) { tmp = ttmin; ttmin = ttmax; ttmax = tmp; }
+    h.tmin = cl_max(ttmin, h.tmin);
+    h.tmax = cl_min(ttmax, h.tmax);
+    if (h.tmin > h.tmax) return h;
+    ttmin = (box.pmin.z - o.z) / d.z;
+    ttmax = (box.pmax.z - o.z) / d.z;
+    if (d.z < 0) { tmp = ttmin; ttmin = ttmax; ttmax = tmp; }
+    h.tmin = cl_max(ttmin, h.tmin);
+    h.tmax = cl_min(ttmax, h.tmax);
+    if (h.tmin > h.tmax) return h;
+    h.v = true;
+    return h;
+}
+
+// A10/code.cl:199-242 (A07-A10 form: stored w = r^2, inclusive range test).
+// `a` = dot(d,d) is loop-invariant and hoisted by the caller (same value every call).
+RT_DEV bool interSphere(f3 o, f3 d, float a_dd, float mint, float maxt, float4 s, float& t_out) {
+    f3 omc = o - mk3(s.x, s.y, s.z);
+    float a = a_dd;
+    float b = 2.0f * dot(omc, d);
+    float c = dot(omc, omc) - s.w;
+    float dis = fmaf(-4.0f * c, a, b * b);
+    if (dis < 0.0f) return false;
+    a = 1.0f / (2.0f * a);
+    dis = sqrtf(dis);
+    float t0 = (-b - dis) * a;
+    float t1 = (-b + dis) * a;
+    float tmin = fminf(t0, t1);
+    float tmax = fmaxf(t0, t1);
+    if (tmin >= mint && tmin <= maxt) { t_out = tmin; return true; }
+    if (tmax >= mint && tmax <= maxt) { t_out = tmax; return true; }
+    return false;
+}
+
+// A10/code.cl:250-288 (INCL = true: A08-A10 inclusive `>= / <=`; false: A07/code.cl:195
+// exclusive `> / <`).  One-sided: rejects div <= 0.
+template <bool INCL>
+RT_DEV bool interTriangle(f3 o, f3 d, float mint, float maxt, f3 p0, f3 p1, f3 p2, float& beta_o, float& gamma_o, float& t_out) {
+    f3 e1 = p1 - p0;
+    f3 e2 = p2 - p0;
+    float div = dot(cross(e2, e1), d);
+    if (div <= 0) return false;
+    float idiv = 1.0f / div;
+    f3 s = o - p0;
+    float beta = dot(cross(s, d), e2) * idiv;
+    if (beta < 0.0f || beta > 1.0f) return false;
+    float gamma = dot(cross(s, e1), d) * idiv;
+    if (gamma < 0.0f || (gamma + beta) < 0.0f || (gamma + beta) > 1.0f) return false;
+    float t = dot(cross(s, e2), e1) * -idiv;
+    bool ok = INCL ? (t >= mint && t <= maxt) : (t > mint && t < maxt);
+    if (!ok) return false;
+    beta_o = beta;
+    gamma_o = gamma;
+    t_out = t;
+    return true;
+}
+
+// A10/code.cl:391-403 (no t > 0 test -- quirk Q5).
+RT_DEV bool interLight(f3 o, f3 d, f3 light_pos, f3 light_normal, float radius, float& t_out) {
+    float den = dot(d, light_normal);
+    if (den == 0.0f) return false;
+    float num = dot((light_pos - o), light_normal);
+    if (num == 0.0f) return false;
+    float t = num / den;
+    f3 poi = getPoint(o, d, t);
+    if (distance(poi, light_pos) > radius) return false;
+    t_out = t;
+    return true;
+}
+
+// A10/code.cl:409-411.
+RT_DEV f3 interp(float beta, float gamma, f3 v1, f3 v2, f3 v3) {
+    return (1.0f - beta - gamma) * v1 + beta * v2 + gamma * v3;
+}
+
+// ---------------------------------------------------------------------------------------
+// RNG -- A10/code.cl:420-434 (quirk Q6: 32-bit wrapping product, signed %, fabs)
+// ---------------------------------------------------------------------------------------
+RT_DEV float nextRand(int& seed) {
+    int s = (int)((unsigned)seed * 16807u);
+    seed = (int)((long long)s % 2147483647LL);
+    const float im = 1.0f / 2147483647.0f;
+    return fabsf((float)seed * im);
+}
+
+// ---------------------------------------------------------------------------------------
+// 3D-DDA walk over the uniform grid (A10/code.cl:694-786 and its four textual copies)
+// ---------------------------------------------------------------------------------------
+struct GridView {
+    const float4* prim;      // spheres: 1 float4 per ref; triangles: 3 float4 per ref
+    const unsigned* box;     // n^3 + 1 exclusive prefix sums
+    AABB bound;
+    unsigned n;
+};
+
+struct Hit {
+    float t;          // champ_t
+    unsigned i;       // champ_i (reference index inside this set), 0xFFFFFFFF = none
+    float beta, gamma;
+    int cx, cy, cz;   // champ_slab (A07 debug colouring)
+};
+
+struct WalkStats { unsigned long long cells, tests; };
+
+enum PrimKind { PRIM_SPHERE = 0, PRIM_TRIANGLE = 1 };
+
+// One axis of the DDA preparation, A10/code.cl:696-707.
+struct Axis {
+    float t_next, delta_t;
+    int slab, step, limit;
+};
+RT_DEV Axis ddaAxis(float o, float d, float tmin, float pmin, float pmax, unsigned n) {
+    Axis a;
+    float x = o + tmin * d;
+    float delta = (pmax - pmin) / (float)n;
+    int slab = (int)((x - pmin) / delta);
+    if (slab < 0) slab = 0;
+    if ((unsigned)slab >= n) slab = (int)n - 1;
+    a.step = (d >= 0) ? 1 : -1;
+    a.limit = (d >= 0) ? (int)n : -1;
+    a.delta_t = delta / fabsf(d);
+    float nxt = pmin + (float)(slab + ((d >= 0) ? 1 : 0)) * delta;
+    a.t_next = (nxt - o) / d;
+    a.slab = slab;
+    return a;
+}
+
+// Closest-hit (ANY = false) or any-hit (ANY = true) walk.  `maxt_in` is the STORED
+// ray.maxt (champ_t starts there).  Returns hit.i != ~0u when a primitive was accepted.
+template <int PRIM, bool ANY, bool TRI_INCL, bool STATS>
+RT_DEV Hit gridWalk(f3 o, f3 d, float maxt_in, const GridView& g, const AabbHit& binter, WalkStats* st) {
+    Axis ax = ddaAxis(o.x, d.x, binter.tmin, g.bound.pmin.x, g.bound.pmax.x, g.n);
+    Axis ay = ddaAxis(o.y, d.y, binter.tmin, g.bound.pmin.y, g.bound.pmax.y, g.n);
+    Axis az = ddaAxis(o.z, d.z, binter.tmin, g.bound.pmin.z, g.bound.pmax.z, g.n);
+    Hit h;
+    h.t = maxt_in;
+    h.i = 0xFFFFFFFFu;
+    h.beta = 0.f; h.gamma = 0.f;
+    h.cx = h.cy = h.cz = (int)g.n;
+    float t = binter.tmin;
+    const unsigned zs = g.n * g.n, ys = g.n;
+    float a_dd = 0.f;
+    if (PRIM == PRIM_SPHERE) a_dd = dot(d, d);
+    while (true) {
+        float mint = t;
+        float maxt = cl_min(cl_min(ax.t_next, ay.t_next), az.t_next);
+        unsigned cell = (unsigned)az.slab * zs + (unsigned)ay.slab * ys + (unsigned)ax.slab;
+        unsigned begin = __ldg(g.box + cell);
+        unsigned end = __ldg(g.box + cell + 1);
+        if (STATS) st->cells++;
+        for (unsigned i = begin; i < end; i++) {
+            float ti;
+            bool v;
+            float be = 0.f, ga = 0.f;
+            if (PRIM == PRIM_SPHERE) {
+                float4 s = __ldg(g.prim + i);
+                v = interSphere(o, d, a_dd, mint, maxt, s, ti);
+            } else {
+                float4 q0 = __ldg(g.prim + 3 * i), q1 = __ldg(g.prim + 3 * i + 1), q2 = __ldg(g.prim + 3 * i + 2);
+                v = interTriangle<TRI_INCL>(o, d, mint, maxt, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z),
+                                            mk3(q2.x, q2.y, q2.z), be, ga, ti);
+            }
+            if (STATS) st->tests++;
+            if (v && ti < h.t) {
+                h.t = ti;
+                h.i = i;
+                h.beta = be;
+                h.gamma = ga;
+                h.cx = ax.slab; h.cy = ay.slab; h.cz = az.slab;
+                if (ANY) break;
+            }
+        }
+        if (h.i != 0xFFFFFFFFu) break;
+        t = maxt;
+        if (t == ax.t_next) {
+            ax.t_next += ax.delta_t;
+            if (t >= binter.tmax) break;
+            ax.slab += ax.step;
+            if (ax.slab == ax.limit) break;
+        } else if (t == ay.t_next) {
+            ay.t_next += ay.delta_t;
+            if (t >= binter.tmax) break;
+            ay.slab += ay.step;
+            if (ay.slab == ay.limit) break;
+        } else {
+            az.t_next += az.delta_t;
+            if (t >= binter.tmax) break;
+            az.slab += az.step;
+            if (az.slab == az.limit) break;
+        }
+    }
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------
+// A10 shading helpers
+// ---------------------------------------------------------------------------------------
+// getHemisphereRay, A10/code.cl:545-579.  Draws s.x then s.y.
+RT_DEV void getHemisphereRay(f3 p, f3 normal, int& seed, f3& o, f3& d) {
+    f3 N = mk3(fabsf(normal.x), fabsf(normal.y), fabsf(normal.z));
+    f3 B = normal;
+    float nmin = cl_min(cl_min(N.x, N.y), N.z);
+    if (N.x == nmin) B.x = 1.0f;
+    else if (N.y == nmin) B.y = 1.0f;
+    else B.z = 1.0f;
+    N = normal;
+    B = normalize(B);
+    f3 T = cross(B, N);
+    B = cross(N, T);
+    f2 sxy;
+    sxy.x = nextRand(seed);
+    sxy.y = nextRand(seed);
+    sxy = concentric_distort(sxy);
+    float sz = sqrtf(cl_max(0.0f, 1.0f - sxy.x * sxy.x - sxy.y * sxy.y));
+    o = p;
+    d = normalize(sxy.x * T + sxy.y * B + sz * N);
+}
+
+// initShadowTrace body for a live hit record, A10/code.cl:652-672.  Draws x then y.
+RT_DEV RayR makeShadowRay(f3 p, f3 normal, const LightArg& L, int& seed) {
+    f3 light_pos = mk3(L.v[0], L.v[1], L.v[2]);
+    f3 T = mk3(L.v[3], L.v[4], L.v[5]);
+    f3 B = mk3(L.v[6], L.v[7], L.v[8]);
+    float light_radius = L.v[9];
+    p = p + normal * 0.001f;
+    f2 xy;
+    xy.x = nextRand(seed);
+    xy.y = nextRand(seed);
+    xy = concentric_distort(xy);
+    xy.x = xy.x * light_radius;
+    xy.y = xy.y * light_radius;
+    light_pos = light_pos + (xy.x * T + xy.y * B);
+    return makeRay(p, light_pos);
+}
+
+// sceneRender shade term, A10/code.cl:1343-1357.  `lit` = shadow.maxt != shadow.mint.
+RT_DEV f3 neeShade(f3 p, f3 normal, f3 shadow_d, bool lit, const LightArg& L) {
+    f3 shade = mk3(0.0f, 0.0f, 0.0f);
+    if (lit) {
+        f3 lpos = mk3(L.v[0], L.v[1], L.v[2]);
+        f3 lnor = mk3(L.v[3], L.v[4], L.v[5]);
+        f3 es = mk3(L.v[6], L.v[7], L.v[8]);
+        float area = L.v[9];
+        float r = distance(p, lpos);
+        float cosx = cl_clamp(dot(shadow_d, normal), 0.0f, 1.0f);
+        float cosy = cl_clamp(dot(-shadow_d, lnor), 0.0f, 1.0f);
+        shade = area * ((cosx * cosy) / (r * r)) * es;
+    }
+    return shade;
+}
+
+}  // namespace rt

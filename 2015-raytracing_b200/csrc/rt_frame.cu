@@ -1,0 +1,436 @@
+// rt_frame.cu -- scene object and progressive path-tracing renderer behind the C ABI.
+// Mirrors preRender / executeRender / postRender of Assign10-Path_Tracing/code.js:1784-1859.
+//
+// Ray slots are independent (every reference kernel indexes only its own slot id), so the
+// frame is processed in TILES of consecutive slots whose ray/hit/shadow state fits the L2;
+// only the per-slot seed and accumulation buffers persist across passes, exactly as in the
+// reference (acu is never cleared between passes, A10/code.js:1078-1099).
+#include "rt_device.cuh"
+#include "rt_internal.h"
+
+using namespace rt;
+
+struct SceneSet {
+    rt_grid grid;
+    float bound[8];
+    int is_mesh;
+    unsigned mesh_matid;
+};
+struct SceneLight { float shadow[16], scene[16], light[16]; };
+
+struct rt_scene {
+    rt_ctx* ctx = nullptr;
+    float bound[8] = {0};
+    std::vector<SceneSet> sets;
+    std::vector<SceneLight> lights;
+    void* materials = nullptr;
+    unsigned n_materials = 0;
+};
+
+struct rt_render {
+    rt_ctx* ctx = nullptr;
+    rt_scene* scene = nullptr;
+    rt_render_opts o{};
+    unsigned slots_pp = 0;           // slots per pixel handled by this context
+    size_t pixels = 0, local_slots = 0;
+    size_t tile_slots = 0;           // multiple of slots_pp
+    // persistent
+    int* seeds = nullptr;            // [pixel][k_local]
+    float4* acu = nullptr;           // [pixel][k_local]
+    float4* accum = nullptr;         // [pixel] sum over k_local
+    uchar4* pixel = nullptr;
+    bool have_seeds = false;
+    unsigned passes = 1;             // the reference starts at 1 and divides by it (A10/code.js:416,1850)
+    // per tile
+    Ray* rays = nullptr;
+    Poi10* pois = nullptr;
+    Ray* shadow = nullptr;
+    // stats
+    unsigned long long* d_counters = nullptr;   // [0] closest rays, [1] any rays
+    unsigned long long h_counters[2] = {0, 0};
+    unsigned last_launches = 0;
+    float last_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+constexpr unsigned kBlock = 256;
+
+// Tile-aware initTrace (A10/code.cl:458-543): local slot id -> (pixel, global k).
+__global__ void f_initTrace(Ray* rays, Poi10* pois, AabbArg bound_a, CamArg fcam, float focal_length, float lens_rad,
+                            unsigned rays_per_pixel, unsigned slot_begin, unsigned slots_pp, size_t pixel_base, unsigned n_local,
+                            const float2* rpp1_coords) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n_local) return;
+    Camera cam = floatToCamera(fcam.v);
+    AABB bound = toAABB(bound_a);
+    size_t pix = pixel_base + id / slots_pp;
+    unsigned k = slot_begin + id % slots_pp;
+    unsigned col = (unsigned)(pix % cam.cols), row = (unsigned)(pix / cam.cols);
+    float4* pq = reinterpret_cast<float4*>(pois + id);
+    pq[2] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    pois[id].matId = -1;
+    f2 coord;
+    if (rays_per_pixel > 1) {
+        unsigned side = (unsigned)sqrtf((float)rays_per_pixel);
+        if (k >= side * side) { storeDeadRay(rays + id); return; }
+        unsigned i = k / side, j = k % side;
+        float delta = 1.0f / (float)side;
+        coord.y = delta / 2.0f;
+        for (unsigned a = 0; a < i; a++) coord.y += delta;
+        coord.x = delta / 2.0f;
+        for (unsigned a = 0; a < j; a++) coord.x += delta;
+    } else {
+        float2 c = rpp1_coords[pix];
+        coord.x = c.x;
+        coord.y = c.y;
+    }
+    f3 focal_point = getFocalPoint(cam, (float)col, (float)row, focal_length);
+    RayR ray;
+    getThinLensRay(cam, focal_point, lens_rad, coord, ray.o, ray.d);
+    AabbHit inter = interAABB(ray.o, ray.d, bound);
+    if (inter.v) { ray.mint = inter.tmin; ray.maxt = inter.tmax; }
+    else { ray.mint = RT_INF; ray.maxt = RT_INF; }
+    storeRay(rays + id, ray);
+}
+
+// rpp == 1 seeds (quirk Q7, see rt_kernels_a10.cu): column `col` serves its rows in order.
+__global__ void f_rpp1_coords(int* seeds, float2* coords, unsigned cols, unsigned rows) {
+    unsigned col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    int seed = seeds[col];
+    for (unsigned row = 0; row < rows; row++) {
+        float y = nextRand(seed);
+        float x = nextRand(seed);
+        coords[(size_t)row * cols + col] = make_float2(x, y);
+    }
+    seeds[col] = seed;
+}
+
+__global__ void f_countValid(const Ray* rays, unsigned n, unsigned long long* counter) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = false;
+    if (id < n) {
+        float4 c = reinterpret_cast<const float4*>(rays + id)[2];
+        valid = c.x != c.y;
+    }
+    unsigned b = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(counter, (unsigned long long)__popc(b));
+}
+
+// accum[pixel] = sum_k acu[pixel][k] in k order (the summation of copyToPixel, A10/code.cl:1376-1380)
+__global__ void f_sumSlots(const float4* acu, float4* accum, size_t pixels, unsigned slots_pp) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= pixels) return;
+    const float4* a = acu + id * slots_pp;
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (unsigned i = 0; i < slots_pp; i++) {
+        float4 v = a[i];
+        c.x += v.x; c.y += v.y; c.z += v.z; c.w += v.w;
+    }
+    accum[id] = c;
+}
+
+// copyToPixel tail on a per-pixel sum (A10/code.cl:1381-1384).
+__global__ void f_accumToPixel(uchar4* pixel, const float4* accum, float m, unsigned pixels) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= pixels) return;
+    float4 color = accum[id];
+    float s = 255.0f * m;
+    color.x *= s; color.y *= s; color.z *= s;
+    color.x *= 1.8f; color.y *= 1.8f; color.z *= 1.8f;
+    color.x = cl_clamp(color.x, 0.0f, 255.0f);
+    color.y = cl_clamp(color.y, 0.0f, 255.0f);
+    color.z = cl_clamp(color.z, 0.0f, 255.0f);
+    pixel[id] = make_uchar4((unsigned char)color.x, (unsigned char)color.y, (unsigned char)color.z, 255);
+}
+
+#define RT_TRY(expr)              \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc) return _rc;      \
+    } while (0)
+
+int closestAll(rt_render* r, unsigned n, Poi10* pois, Ray* rays) {
+    rt_ctx* ctx = r->ctx;
+    f_countValid<<<rt_blocks(n, kBlock), kBlock, 0, ctx->stream>>>(rays, n, r->d_counters + 0);
+    RT_LAUNCH_CHECK(ctx, "countValid");
+    for (const SceneSet& s : r->scene->sets) {
+        if (s.grid.kind == 0)
+            RT_TRY(rt_a10_sphereTrace(ctx, n, pois, rays, s.grid.prim, s.grid.matid, s.grid.box_size, s.bound, s.grid.n_slabs));
+        else if (!s.is_mesh)
+            RT_TRY(rt_a10_triangleTrace(ctx, n, pois, rays, s.grid.prim, s.grid.normal, s.grid.matid, s.grid.box_size, s.bound, s.grid.n_slabs));
+        else
+            RT_TRY(rt_a10_meshTrace(ctx, n, pois, rays, s.grid.prim, s.grid.normal, s.grid.box_size, s.mesh_matid, s.bound, s.grid.n_slabs));
+    }
+    return RT_OK;
+}
+
+int shadeAll(rt_render* r, unsigned n, Poi10* pois, Ray* shadow, float4* acu, int* seeds) {
+    rt_ctx* ctx = r->ctx;
+    for (const SceneLight& L : r->scene->lights) {
+        RT_TRY(rt_a10_initShadowTrace(ctx, shadow, pois, n, L.shadow, seeds));
+        f_countValid<<<rt_blocks(n, kBlock), kBlock, 0, ctx->stream>>>(shadow, n, r->d_counters + 1);
+        RT_LAUNCH_CHECK(ctx, "countValid");
+        for (const SceneSet& s : r->scene->sets) {
+            if (s.grid.kind == 0)
+                RT_TRY(rt_a10_sphereShadowTrace(ctx, n, shadow, s.grid.prim, s.grid.box_size, s.bound, s.grid.n_slabs));
+            else
+                RT_TRY(rt_a10_triangleShadowTrace(ctx, n, shadow, s.grid.prim, s.grid.box_size, s.bound, s.grid.n_slabs));
+        }
+        RT_TRY(rt_a10_sceneRender(ctx, acu, pois, shadow, r->scene->materials, L.scene, n));
+    }
+    return RT_OK;
+}
+
+// One tile through the reference's kernel sequence (executeRender, A10/code.js:1806-1846).
+int tileReferenceSchedule(rt_render* r, const float* fcam, size_t slot0, unsigned n, const float2* rpp1_coords) {
+    rt_ctx* ctx = r->ctx;
+    const rt_render_opts& o = r->o;
+    AabbArg ba; memcpy(ba.v, r->scene->bound, sizeof ba.v);
+    CamArg ca; memcpy(ca.v, fcam, sizeof ca.v);
+    f_initTrace<<<rt_blocks(n, kBlock), kBlock, 0, ctx->stream>>>(r->rays, r->pois, ba, ca, o.focal_length, o.lens_rad, o.rays_per_pixel,
+                                                                   o.slot_begin, r->slots_pp, slot0 / r->slots_pp, n, rpp1_coords);
+    RT_LAUNCH_CHECK(ctx, "initTrace");
+    float4* acu = r->acu + slot0;
+    int* seeds = r->seeds + slot0;
+    RT_TRY(closestAll(r, n, r->pois, r->rays));
+    for (const SceneLight& L : r->scene->lights) RT_TRY(rt_a10_lightRender(ctx, r->pois, r->rays, acu, L.light, n));
+    RT_TRY(shadeAll(r, n, r->pois, r->shadow, acu, seeds));
+    for (unsigned j = 0; j < o.depth; j++) {
+        RT_TRY(rt_a10_bouncePaths(ctx, r->pois, r->rays, seeds, n));
+        RT_TRY(closestAll(r, n, r->pois, r->rays));
+        RT_TRY(shadeAll(r, n, r->pois, r->shadow, acu, seeds));
+    }
+    return RT_OK;
+}
+
+}  // namespace
+
+// implemented in rt_wavefront.cu (fused wavefront path); returns RT_ERR_STATE if not built
+extern int rt_wavefront_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, const float2* rpp1_coords) __attribute__((weak));
+
+extern "C" {
+
+int rt_scene_create(rt_ctx* ctx, rt_scene** out) {
+    RT_CHECK_CTX(ctx);
+    if (!out) return RT_ERR_INVALID;
+    rt_scene* s = new rt_scene();
+    s->ctx = ctx;
+    *out = s;
+    return RT_OK;
+}
+
+int rt_scene_destroy(rt_scene* s) {
+    if (!s) return RT_ERR_INVALID;
+    if (s->materials) rt_buffer_release(s->ctx, s->materials);
+    delete s;
+    return RT_OK;
+}
+
+int rt_scene_set_bounds(rt_scene* s, const float bound[8]) {
+    if (!s || !bound) return RT_ERR_INVALID;
+    memcpy(s->bound, bound, sizeof s->bound);
+    return RT_OK;
+}
+
+int rt_scene_set_materials(rt_scene* s, const float* rgba, unsigned n_materials) {
+    if (!s || (!rgba && n_materials)) return RT_ERR_INVALID;
+    if (s->materials) { rt_buffer_release(s->ctx, s->materials); s->materials = nullptr; }
+    RT_TRY(rt_buffer_create(s->ctx, sizeof(float) * 4 * (n_materials ? n_materials : 1), &s->materials));
+    if (n_materials) RT_TRY(rt_buffer_write(s->ctx, s->materials, 0, sizeof(float) * 4 * n_materials, rgba));
+    s->n_materials = n_materials;
+    return RT_OK;
+}
+
+int rt_scene_add_set(rt_scene* s, const rt_grid* grid, const float bound[8], int is_mesh, unsigned mesh_matid) {
+    if (!s || !grid || !bound || !grid->box_size || !grid->prim) return RT_ERR_INVALID;
+    if (grid->kind == 1 && !grid->normal) return RT_ERR_INVALID;
+    SceneSet st;
+    st.grid = *grid;
+    memcpy(st.bound, bound, sizeof st.bound);
+    st.is_mesh = is_mesh;
+    st.mesh_matid = mesh_matid;
+    s->sets.push_back(st);
+    return RT_OK;
+}
+
+int rt_scene_add_light(rt_scene* s, const float shadow_info[16], const float scene_info[16], const float light_info[16]) {
+    if (!s || !shadow_info || !scene_info || !light_info) return RT_ERR_INVALID;
+    SceneLight L;
+    memcpy(L.shadow, shadow_info, sizeof L.shadow);
+    memcpy(L.scene, scene_info, sizeof L.scene);
+    memcpy(L.light, light_info, sizeof L.light);
+    s->lights.push_back(L);
+    return RT_OK;
+}
+
+int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, rt_render** out) {
+    RT_CHECK_CTX(ctx);
+    if (!scene || !opts || !out || !opts->cols || !opts->rows || !opts->rays_per_pixel) return RT_ERR_INVALID;
+    if (!scene->materials) return rt_fail(ctx, RT_ERR_STATE, "render: scene has no materials");
+    rt_render* r = new rt_render();
+    r->ctx = ctx;
+    r->scene = scene;
+    r->o = *opts;
+    if (r->o.slot_count == 0) { r->o.slot_begin = 0; r->o.slot_count = r->o.rays_per_pixel; }
+    if (r->o.slot_begin + r->o.slot_count > r->o.rays_per_pixel) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: slot range exceeds rays_per_pixel"); }
+    if (r->o.rays_per_pixel > 1) {
+        unsigned side = (unsigned)sqrtf((float)r->o.rays_per_pixel);
+        if (side * side != r->o.rays_per_pixel) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: rays_per_pixel must be a perfect square"); }
+    }
+    r->slots_pp = r->o.slot_count;
+    r->pixels = (size_t)r->o.cols * r->o.rows;
+    r->local_slots = r->pixels * r->slots_pp;
+    if ((unsigned long long)r->pixels * r->o.rays_per_pixel > 0xFFFFFFFFull) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: total_rays exceeds the reference's uint range"); }
+    size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)1 << 20;
+    size_t px_per_tile = want / r->slots_pp;
+    if (px_per_tile == 0) px_per_tile = 1;
+    if (px_per_tile > r->pixels) px_per_tile = r->pixels;
+    r->tile_slots = px_per_tile * r->slots_pp;
+    int rc = RT_OK;
+    auto A = [&](void** p, size_t bytes) { if (!rc) rc = rt_buffer_create(ctx, bytes, p); };
+    A((void**)&r->seeds, sizeof(int) * r->local_slots);
+    A((void**)&r->acu, sizeof(float4) * r->local_slots);
+    A((void**)&r->accum, sizeof(float4) * r->pixels);
+    A((void**)&r->pixel, sizeof(uchar4) * r->pixels);
+    A((void**)&r->rays, sizeof(Ray) * r->tile_slots);
+    A((void**)&r->pois, sizeof(Poi10) * r->tile_slots);
+    A((void**)&r->shadow, sizeof(Ray) * r->tile_slots);
+    A((void**)&r->d_counters, sizeof(unsigned long long) * 2);
+    if (!rc && (cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess)) rc = RT_ERR_CUDA;
+    // prepareInitAcu (A10/code.js:1078-1099): zero once, never again between passes
+    if (!rc) rc = rt_buffer_fill(ctx, r->acu, 0, sizeof(float4) * r->local_slots);
+    if (!rc) rc = rt_buffer_fill(ctx, r->pois, 0, sizeof(Poi10) * r->tile_slots);
+    if (!rc) rc = rt_buffer_fill(ctx, r->rays, 0, sizeof(Ray) * r->tile_slots);
+    if (rc) { rt_render_destroy(r); return rc; }
+    *out = r;
+    return RT_OK;
+}
+
+int rt_render_destroy(rt_render* r) {
+    if (!r) return RT_ERR_INVALID;
+    rt_ctx* ctx = r->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rays, r->pois, r->shadow, r->d_counters};
+    for (void* b : bufs) if (b) cudaFree(b);
+    if (r->ev0) cudaEventDestroy(r->ev0);
+    if (r->ev1) cudaEventDestroy(r->ev1);
+    delete r;
+    return RT_OK;
+}
+
+namespace {
+// global seed array [pixel][k] -> this context's [pixel][k_local]
+__global__ void f_sliceSeeds(const int* global_seeds, int* local, size_t pixels, unsigned rpp, unsigned slot_begin, unsigned slots_pp) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= pixels * slots_pp) return;
+    size_t pix = id / slots_pp;
+    unsigned k = slot_begin + (unsigned)(id % slots_pp);
+    local[id] = global_seeds[pix * rpp + k];
+}
+}  // namespace
+
+int rt_render_set_seeds(rt_render* r, const int* seeds, size_t count, int on_device) {
+    if (!r || !seeds) return RT_ERR_INVALID;
+    rt_ctx* ctx = r->ctx;
+    const rt_render_opts& o = r->o;
+    size_t total = r->pixels * o.rays_per_pixel;
+    if (count != total) return rt_fail(ctx, RT_ERR_INVALID, "set_seeds: count must be cols*rows*rays_per_pixel");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (r->slots_pp == o.rays_per_pixel) {
+        RT_CUDA(ctx, cudaMemcpyAsync(r->seeds, seeds, sizeof(int) * total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    } else if (on_device) {
+        f_sliceSeeds<<<rt_blocks(r->local_slots, kBlock), kBlock, 0, ctx->stream>>>(seeds, r->seeds, r->pixels, o.rays_per_pixel, o.slot_begin, r->slots_pp);
+        RT_LAUNCH_CHECK(ctx, "sliceSeeds");
+    } else {
+        // strided host -> device copy: one 2-D copy, row = pixel, width = this context's slot range
+        RT_CUDA(ctx, cudaMemcpy2DAsync(r->seeds, sizeof(int) * r->slots_pp, seeds + o.slot_begin, sizeof(int) * o.rays_per_pixel,
+                                       sizeof(int) * r->slots_pp, r->pixels, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    r->have_seeds = true;
+    return RT_OK;
+}
+
+int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pixels) {
+    if (!r || !fcam) return RT_ERR_INVALID;
+    rt_ctx* ctx = r->ctx;
+    const rt_render_opts& o = r->o;
+    if (!r->have_seeds) return rt_fail(ctx, RT_ERR_STATE, "render_execute: seeds not set (rt_render_set_seeds)");
+    if ((unsigned)fcam[14] != o.cols || (unsigned)fcam[15] != o.rows) return rt_fail(ctx, RT_ERR_INVALID, "render_execute: camera cols/rows differ from the render's");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long launches0 = ctx->launches;
+    RT_CUDA(ctx, cudaMemsetAsync(r->d_counters, 0, sizeof(unsigned long long) * 2, ctx->stream));
+    RT_CUDA(ctx, cudaEventRecord(r->ev0, ctx->stream));
+    float2* coords = nullptr;
+    if (o.rays_per_pixel == 1) {
+        RT_CUDA(ctx, cudaMallocAsync((void**)&coords, sizeof(float2) * r->pixels, ctx->stream));
+        f_rpp1_coords<<<rt_blocks(o.cols, 64), 64, 0, ctx->stream>>>(r->seeds, coords, o.cols, o.rows);
+        RT_LAUNCH_CHECK(ctx, "initTrace(seeds)");
+    }
+    for (size_t slot0 = 0; slot0 < r->local_slots; slot0 += r->tile_slots) {
+        size_t rem = r->local_slots - slot0;
+        unsigned n = (unsigned)(rem < r->tile_slots ? rem : r->tile_slots);
+        int rc;
+        if (o.mode == 0 && rt_wavefront_tile) rc = rt_wavefront_tile(r, fcam, slot0, n, coords);
+        else rc = tileReferenceSchedule(r, fcam, slot0, n, coords);
+        if (rc) return rc;
+    }
+    if (coords) RT_CUDA(ctx, cudaFreeAsync(coords, ctx->stream));
+    f_sumSlots<<<rt_blocks(r->pixels, kBlock), kBlock, 0, ctx->stream>>>(r->acu, r->accum, r->pixels, r->slots_pp);
+    RT_LAUNCH_CHECK(ctx, "sumSlots");
+    RT_CUDA(ctx, cudaEventRecord(r->ev1, ctx->stream));
+    if (host_pixels) {
+        // executeCopyToPixel(passes): m = 1/(rays_per_pixel*passes) rounded to fp32 (A10/code.js:1410-1415)
+        float m = (float)(1.0 / ((double)o.rays_per_pixel * (double)r->passes));
+        f_accumToPixel<<<rt_blocks(r->pixels, kBlock), kBlock, 0, ctx->stream>>>(r->pixel, r->accum, m, (unsigned)r->pixels);
+        RT_LAUNCH_CHECK(ctx, "copyToPixel");
+        RT_CUDA(ctx, cudaMemcpyAsync(host_pixels, r->pixel, sizeof(uchar4) * r->pixels, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    RT_CUDA(ctx, cudaMemcpyAsync(r->h_counters, r->d_counters, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(ctx, cudaEventElapsedTime(&r->last_ms, r->ev0, r->ev1));
+    r->last_launches = (unsigned)(ctx->launches - launches0);
+    r->passes++;
+    return RT_OK;
+}
+
+int rt_render_accum_image(rt_render* r, void** dptr_float4) {
+    if (!r || !dptr_float4) return RT_ERR_INVALID;
+    *dptr_float4 = r->accum;
+    return RT_OK;
+}
+
+int rt_render_read_accum(rt_render* r, float* host_float4) {
+    if (!r || !host_float4) return RT_ERR_INVALID;
+    return rt_buffer_read(r->ctx, r->accum, 0, sizeof(float4) * r->pixels, host_float4);
+}
+
+int rt_render_read_seeds(rt_render* r, int* host_seeds, size_t count) {
+    if (!r || !host_seeds) return RT_ERR_INVALID;
+    if (count != r->local_slots) return rt_fail(r->ctx, RT_ERR_INVALID, "read_seeds: count must be cols*rows*slot_count");
+    return rt_buffer_read(r->ctx, r->seeds, 0, sizeof(int) * count, host_seeds);
+}
+
+int rt_accum_to_pixel(rt_ctx* ctx, void* pixel, const void* accum_float4, float m, unsigned pixels) {
+    RT_CHECK_CTX(ctx);
+    if (!pixel || !accum_float4) return RT_ERR_INVALID;
+    if (!pixels) return RT_OK;
+    f_accumToPixel<<<rt_blocks(pixels, kBlock), kBlock, 0, ctx->stream>>>((uchar4*)pixel, (const float4*)accum_float4, m, pixels);
+    RT_LAUNCH_CHECK(ctx, "accumToPixel");
+    return RT_OK;
+}
+
+int rt_render_stats(rt_render* r, unsigned long long* closest_rays, unsigned long long* any_rays, unsigned* launches, float* device_ms) {
+    if (!r) return RT_ERR_INVALID;
+    if (closest_rays) *closest_rays = r->h_counters[0];
+    if (any_rays) *any_rays = r->h_counters[1];
+    if (launches) *launches = r->last_launches;
+    if (device_ms) *device_ms = r->last_ms;
+    return RT_OK;
+}
+
+}  // extern "C"

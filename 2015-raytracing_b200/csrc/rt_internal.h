@@ -1,0 +1,55 @@
+// rt_internal.h -- host-side internals shared by the translation units of librt2015.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rt2015.h"
+
+struct rt_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string last_error;
+    // optional per-work-item walk statistics (device pointers, may be null)
+    unsigned* st_hit = nullptr;
+    unsigned* st_cells = nullptr;
+    unsigned* st_tests = nullptr;
+    unsigned long long launches = 0;   // kernels launched through this context
+};
+
+#define RT_CHECK_CTX(ctx)              \
+    do {                               \
+        if (!(ctx)) return RT_ERR_INVALID; \
+    } while (0)
+
+static inline int rt_fail(rt_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (ctx) {
+        char buf[512];
+        if (e != cudaSuccess)
+            snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+        else
+            snprintf(buf, sizeof buf, "%s", what);
+        ctx->last_error = buf;
+    }
+    return code;
+}
+
+#define RT_CUDA(ctx, call)                                         \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return rt_fail(ctx, RT_ERR_CUDA, #call, _e); \
+    } while (0)
+
+// Check the launch that was just issued.
+#define RT_LAUNCH_CHECK(ctx, name)                                 \
+    do {                                                           \
+        (ctx)->launches++;                                         \
+        cudaError_t _e = cudaGetLastError();                       \
+        if (_e != cudaSuccess) return rt_fail(ctx, RT_ERR_CUDA, name, _e); \
+    } while (0)
+
+static inline unsigned rt_blocks(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }

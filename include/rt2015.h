@@ -1,0 +1,186 @@
+/* rt2015.h -- C ABI of librt2015.so, the B200 (sm_100a) implementation of the data-parallel
+ * hot path of eaymerich/2015-RayTracing.
+ *
+ * This is the drop-in boundary: it replaces the WebCL object model the reference's host
+ * code drives (context / queue / program / kernel / buffer; call sites
+ * Assign10-Path_Tracing/code.js:576-608, 1047-1099, 1101-1552) with plain C entry points
+ * a Node N-API addon, a cgo/JNI stub or Python ctypes can bind directly.  There are no C++
+ * or torch types in any signature: device memory is an opaque `void*` (a CUDA device
+ * pointer; memory allocated elsewhere in the same CUDA context, e.g. by a tensor library,
+ * may be passed as well), small by-value kernel arguments of the reference (camera
+ * `float16`, light `float16`, `AABB`) are host `const float*`.
+ *
+ * Three layers, each citing what it replaces (paths relative to /root/reference,
+ * A07/A08/A09/A10 = the assignment directories):
+ *   1. context + buffers      = webcl.createContext / createBuffer / enqueue{Write,Read}Buffer
+ *   2. one launcher per kernel = createKernel + setArg + enqueueNDRangeKernel, argument
+ *                                order and struct layouts of code.cl kept
+ *   3. grid build + scene + render = split*Data / preRender / executeRender / postRender
+ *
+ * Conventions: every function returns 0 on success or a negative rt_status; launchers are
+ * asynchronous on the context's single in-order stream (the reference uses one in-order
+ * command queue, A10/code.js:592); rt_finish / rt_buffer_read synchronise.  A context is
+ * not thread-safe (neither is the reference); contexts on different GPUs are independent.
+ */
+#ifndef RT2015_H
+#define RT2015_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,      /* bad argument */
+    RT_ERR_CUDA = -2,         /* CUDA runtime error, see rt_last_error_string */
+    RT_ERR_NOMEM = -3,
+    RT_ERR_NO_DEVICE = -4,    /* no usable CUDA device: there is NO CPU fallback */
+    RT_ERR_STATE = -5         /* call order violated (e.g. execute before seeds) */
+} rt_status;
+
+typedef struct rt_ctx rt_ctx;
+typedef struct rt_scene rt_scene;
+typedef struct rt_render rt_render;
+
+/* ---- 1. context and buffers ------------------------------------------------------------ */
+/* createCLBasicResources, A10/code.js:576-608 */
+int rt_ctx_create(int device_ordinal, rt_ctx** out);
+int rt_ctx_destroy(rt_ctx* ctx);                                  /* releaseCLResources :1539-1552 */
+const char* rt_last_error_string(rt_ctx* ctx);                    /* program build log / exceptions */
+int rt_finish(rt_ctx* ctx);                                       /* cmdQueue.finish() */
+void* rt_ctx_stream(rt_ctx* ctx);                                 /* the cudaStream_t launches go to */
+int rt_device_info(rt_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* l2_bytes, size_t* total_mem);
+
+int rt_buffer_create(rt_ctx* ctx, size_t bytes, void** dptr);     /* ctx.createBuffer */
+int rt_buffer_release(rt_ctx* ctx, void* dptr);                   /* buffer.release() */
+int rt_buffer_write(rt_ctx* ctx, void* dptr, size_t offset, size_t bytes, const void* host);   /* enqueueWriteBuffer */
+int rt_buffer_read(rt_ctx* ctx, const void* dptr, size_t offset, size_t bytes, void* host);    /* enqueueReadBuffer + finish */
+int rt_buffer_fill(rt_ctx* ctx, void* dptr, int byte_value, size_t bytes);
+
+/* sizeofRay / sizeofPoi probe kernels, A10/code.cl:440-446, A10/code.js:1064-1076.
+ * name = "Ray" | "Poi"; assignment = 3,7,8,9,10.  Returns 0 for an unknown struct. */
+unsigned rt_struct_size(const char* name, int assignment);
+
+/* ---- 2. one launcher per reference kernel ------------------------------------------------
+ * Pointer arguments are device pointers; `bound` = 8 floats (pmin.xyz,1,pmax.xyz,1 as
+ * bounds2AABB packs them, A10/code.js:610-621); `fcam`/`light_info` = 16 floats. */
+
+/* Assignment 10 (A10/code.cl) */
+int rt_a10_initAcu(rt_ctx*, void* acu, unsigned total_rays);                                           /* :448-456 */
+int rt_a10_initTrace(rt_ctx*, void* seeds, void* rays, void* pois, const float* bound, const float* fcam,
+                     float focal_length, float lens_rad, unsigned rays_per_pixel);                     /* :458-543 */
+int rt_a10_bouncePaths(rt_ctx*, void* pois, void* rays, void* seeds, unsigned total_rays);             /* :581-598 */
+int rt_a10_lightRender(rt_ctx*, void* pois, void* rays, void* acu, const float* light_info, unsigned total_rays);   /* :600-629 */
+int rt_a10_initShadowTrace(rt_ctx*, void* shadow_rays, void* pois, unsigned total_rays, const float* light_info,
+                           void* seeds);                                                               /* :631-673 */
+int rt_a10_sphereTrace(rt_ctx*, unsigned total_rays, void* pois, void* rays, const void* spheres, const void* s_matid,
+                       const void* s_box_size, const float* bound, unsigned n_slabs);                  /* :675-800 */
+int rt_a10_triangleTrace(rt_ctx*, unsigned total_rays, void* pois, void* rays, const void* t_pos, const void* t_normal,
+                         const void* t_matid, const void* t_box_size, const float* bound, unsigned n_slabs);   /* :802-935 */
+int rt_a10_meshTrace(rt_ctx*, unsigned total_rays, void* pois, void* rays, const void* t_pos, const void* t_normal,
+                     const void* t_box_size, unsigned t_matid, const float* bound, unsigned n_slabs);  /* :937-1070 */
+int rt_a10_sphereShadowTrace(rt_ctx*, unsigned total_rays, void* shadow_rays, const void* spheres, const void* s_box_size,
+                             const float* bound, unsigned n_slabs);                                    /* :1073-1193 */
+int rt_a10_triangleShadowTrace(rt_ctx*, unsigned total_rays, void* shadow_rays, const void* t_pos, const void* t_box_size,
+                               const float* bound, unsigned n_slabs);                                  /* :1195-1321 */
+int rt_a10_sceneRender(rt_ctx*, void* acu, void* pois, const void* shadow_rays, const void* material,
+                       const float* light_info, unsigned total_rays);                                  /* :1323-1364 */
+int rt_a10_copyToPixel(rt_ctx*, void* pixel, const void* acu, float m, unsigned pixels, unsigned rays_per_pixel);   /* :1366-1386 */
+
+/* Optional per-work-item statistics for the five grid-walk launchers (all device pointers,
+ * any may be NULL; pass all NULL to switch off): winning reference index (0xFFFFFFFF =
+ * none), cells visited, primitive tests.  Used for hit-id parity and for the algorithmic
+ * byte count of the roofline. */
+int rt_set_walk_stats(rt_ctx*, void* hit_id_u32, void* cells_u32, void* tests_u32);
+
+/* ---- 3. grid build, scene, render ---------------------------------------------------------
+ * Uniform-grid build = splitSphereData / splitTriangleData / splitMeshData
+ * (A10/code.js:1554-1641, 1643-1772, 899-1041; A07/code.js:889-1122) as integer CUDA kernels
+ * (count -> exclusive scan -> order-preserving scatter), binning in float64 like the
+ * JavaScript.  Inputs are HOST arrays of doubles (JS Numbers).  Outputs are device buffers
+ * owned by the returned rt_grid (release with rt_grid_release). */
+typedef struct {
+    void* prim;          /* spheres: float4 (cx,cy,cz,r*r) per ref; triangles: 3 x float4 (w=0) per ref */
+    void* normal;        /* triangles: 3 x float4 per ref; spheres: NULL */
+    void* matid;         /* uint per ref (material / atom index) or NULL */
+    void* box_size;      /* uint[n^3 + 1] exclusive prefix sums, cell = z*n*n + y*n + x */
+    void* occupancy;     /* internal: 1 bit per cell (non-empty), used by the fused render path */
+    unsigned n_refs;
+    unsigned n_slabs;
+    unsigned kind;       /* 0 = sphere, 1 = triangle */
+    unsigned _reserved;
+} rt_grid;
+
+/* Post-split position transform of Mesh.normalize/scale/translate (A10/code.js:114-169),
+ * applied in float64 to the cell-ordered positions before the fp32 store:
+ *   p = (p - center) * maxdim   (if do_normalize)   ;   p *= scale   ;   p += translate */
+typedef struct {
+    int do_normalize;
+    double center[3];
+    double maxdim;
+    double scale[3];
+    double translate[3];
+} rt_mesh_xform;
+
+/* xyzr: n x 4 doubles (cx,cy,cz,radius); id: n uints (material or atom index) or NULL. */
+int rt_grid_build_spheres(rt_ctx*, const double* xyzr, const unsigned* id, unsigned n, const double bmin[3],
+                          const double bmax[3], unsigned n_slabs, rt_grid* out);
+/* pos9/nor9: n x 9 doubles (three vertices); id: n uints or NULL; xform may be NULL. */
+int rt_grid_build_triangles(rt_ctx*, const double* pos9, const double* nor9, const unsigned* id, unsigned n,
+                            const double bmin[3], const double bmax[3], unsigned n_slabs, const rt_mesh_xform* xform,
+                            rt_grid* out);
+int rt_grid_release(rt_ctx*, rt_grid* g);
+
+/* Scene = what preRender uploads (A10/code.js:1784-1804). */
+int rt_scene_create(rt_ctx*, rt_scene** out);
+int rt_scene_destroy(rt_scene*);
+int rt_scene_set_bounds(rt_scene*, const float bound[8]);                              /* scene.bounds */
+int rt_scene_set_materials(rt_scene*, const float* rgba, unsigned n_materials);        /* splitMaterialData :1774-1782 */
+/* Geometry sets are traced in the order added: spheres, scene triangles, meshes
+ * (executeRender, A10/code.js:1809-1813).  `matid` is used for meshes only (scalar
+ * t_matid of meshTrace); per-reference ids come from grid->matid otherwise. */
+int rt_scene_add_set(rt_scene*, const rt_grid* grid, const float bound[8], int is_mesh, unsigned mesh_matid);
+/* Light.toShadowInfo / toSceneRenderInfo / toLightRenderInfo, A10/code.js:323-352 */
+int rt_scene_add_light(rt_scene*, const float shadow_info[16], const float scene_info[16], const float light_info[16]);
+
+typedef struct {
+    unsigned cols, rows;          /* canvas size */
+    unsigned rays_per_pixel;      /* slots per pixel; > 1 must be a perfect square (stratified lens grid) */
+    unsigned depth;               /* bounces after the primary hit; the reference hard-codes 5 (A10/code.js:1829) */
+    float focal_length;           /* scene.focal_length */
+    float lens_rad;               /* scene.lens_diameter / 2 */
+    unsigned slot_begin, slot_count;   /* multi-GPU: this context renders slots k in [slot_begin, slot_begin+slot_count)
+                                          of every pixel; 0,0 = all rays_per_pixel slots */
+    unsigned mode;                /* 0 = fused wavefront path (default), 1 = reference kernel-by-kernel schedule */
+    unsigned tile_slots;          /* wavefront tile size in ray slots, 0 = auto */
+} rt_render_opts;
+
+/* preRender: allocates ray/hit/accumulation state (A10/code.js:1078-1138, 1417-1442). */
+int rt_render_create(rt_ctx*, rt_scene*, const rt_render_opts* opts, rt_render** out);
+int rt_render_destroy(rt_render*);                                                      /* postRender */
+/* prepareInitSeeds (A10/code.js:1140-1154): `seeds` holds cols*rows*rays_per_pixel ints indexed by
+ * the GLOBAL slot id (pixel*rays_per_pixel + k); host memory unless `on_device` != 0. */
+int rt_render_set_seeds(rt_render*, const int* seeds, size_t count, int on_device);
+/* executeRender (A10/code.js:1806-1854): one progressive pass -- primary rays, lights, `depth`
+ * bounces with next-event estimation, accumulation.  `host_pixels` (cols*rows*4 bytes, RGBA)
+ * receives copyToPixel's image when non-NULL (executeCopyToPixel + sendImagetoHTML). */
+int rt_render_execute(rt_render*, const float fcam[16], unsigned char* host_pixels);
+/* Per-pixel float accumulation image: sum over this context's slots of acu (float4 per pixel,
+ * .w = contribution count).  Device pointer, valid until the next execute/destroy. */
+int rt_render_accum_image(rt_render*, void** dptr_float4);
+int rt_render_read_accum(rt_render*, float* host_float4);                               /* cols*rows*4 floats */
+int rt_render_read_seeds(rt_render*, int* host_seeds, size_t count);                    /* seed state after the pass */
+/* copyToPixel on an accumulation image (after a multi-GPU reduce): m = 1/(rays_per_pixel*passes). */
+int rt_accum_to_pixel(rt_ctx*, void* pixel, const void* accum_float4, float m, unsigned pixels);
+/* Counters of the last execute: valid closest-hit and any-hit queries ("rays"),
+ * kernels launched, device milliseconds between the first and last launch. */
+int rt_render_stats(rt_render*, unsigned long long* closest_rays, unsigned long long* any_rays, unsigned* launches,
+                    float* device_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT2015_H */

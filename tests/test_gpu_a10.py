@@ -1,0 +1,215 @@
+"""GPU parity tests of the Assignment-10 path (grid build, every kernel, the frame) against
+the oracle on the same seeded inputs, all through the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import util
+from oracle import host as OH
+from oracle import refcl as OR
+
+pytestmark = pytest.mark.gpu
+
+COLS, ROWS, RPP = 96, 64, 4
+
+
+@pytest.fixture(scope="module")
+def scenes(tmp_path_factory):
+    return util.make_scene_pair(tmp_path_factory.mktemp("a10"), COLS, ROWS, mesh_uv=(32, 16), mesh_nslabs=10)
+
+
+def _grid_arrays(ctx, rt, g):
+    d = rt.host.DeviceGrid(ctx, g, np.zeros(8, np.float32))
+    out = {"box": d.box_size(), "prim": d.prim(), "matid": d.matid()}
+    if g.kind == 1 and g.normal:
+        out["normal"] = d.normal()
+    return out
+
+
+def test_grid_build_bit_exact(rt, gpu_ctx, scenes):
+    """Cell lists (box_size prefix sums + cell-ordered primitive buffers) must match the
+    reference's JS split*Data bit for bit -- BASELINE.md gate 1."""
+    o_scene, p_scene = scenes
+    prep = OR.prepare_a10(o_scene, 1)
+    # scene triangles / spheres at n_slabs = 1 (A10 default) and at 3 and 5
+    for n in (1, 3, 5):
+        data, mat, box = OH.splitSphereData(o_scene, n)
+        g = rt.splitSphereData(gpu_ctx, p_scene, n)
+        got = _grid_arrays(gpu_ctx, rt, g)
+        assert np.array_equal(got["box"], box)
+        assert np.array_equal(got["prim"].view(np.uint32), OH.to_f32(data).view(np.uint32))
+        assert np.array_equal(got["matid"], mat)
+        rt.lib.dll.rt_grid_release(gpu_ctx.h, C.byref(g))
+        pos, nor, mat, box = OH.splitTriangleData(o_scene, n)
+        g = rt.splitTriangleData(gpu_ctx, p_scene, n)
+        got = _grid_arrays(gpu_ctx, rt, g)
+        assert np.array_equal(got["box"], box)
+        assert np.array_equal(got["prim"].view(np.uint32), OH.to_f32(pos).view(np.uint32))
+        assert np.array_equal(got["normal"].view(np.uint32), OH.to_f32(nor).view(np.uint32))
+        assert np.array_equal(got["matid"], mat)
+        rt.lib.dll.rt_grid_release(gpu_ctx.h, C.byref(g))
+    # the <mesh>: per-mesh nslabs, transform applied after the split in float64
+    om, pm = o_scene["meshes"][0], p_scene["meshes"][0]
+    g = pm.upload(gpu_ctx)
+    got = _grid_arrays(gpu_ctx, rt, g)
+    assert np.array_equal(got["box"], np.asarray(om.boxSizeData, np.uint32))
+    assert np.array_equal(got["prim"].view(np.uint32), OH.to_f32(om.posData).view(np.uint32))
+    assert np.array_equal(got["normal"].view(np.uint32), OH.to_f32(om.normalData).view(np.uint32))
+    assert np.array_equal(rt.bounds2AABB(pm.bounds).view(np.uint32), OH.bounds2AABB(om.bounds).view(np.uint32))
+    assert got["box"][-1] > om.ntriangles  # triangles really are duplicated across cells
+
+
+def _upload_prep(ctx, prep):
+    dev = {"materials": ctx.upload(prep["materials"]), "sets": []}
+    for s in prep["sets"]:
+        d = {"kind": s["kind"], "box": ctx.upload(s["box"]), "aabb": s["aabb"], "n": s["n"]}
+        if s["kind"] == "sphere":
+            d["data"] = ctx.upload(s["data"])
+            d["matid"] = ctx.upload(s["matid"])
+        else:
+            d["pos"] = ctx.upload(s["pos"])
+            d["normal"] = ctx.upload(s["normal"])
+            d["matid"] = ctx.upload(s["matid"]) if s["kind"] == "triangle" else s["matid"]
+        dev["sets"].append(d)
+    return dev
+
+
+def _hp(a):
+    return a.ctypes.data
+
+
+def test_every_kernel_matches_oracle(rt, gpu_ctx, oracle_lib, scenes):
+    """Drive the reference's executeRender schedule kernel by kernel through the C ABI on the
+    GPU and through the oracle on the CPU, on the same uploaded buffers, and compare the
+    device state after EVERY launch."""
+    o_scene, _ = scenes
+    ctx, dll = gpu_ctx, rt.lib.dll
+    prep = OR.prepare_a10(o_scene, 1)
+    dev = _upload_prep(ctx, prep)
+    total = COLS * ROWS * RPP
+    seeds0 = OR.make_seeds(total, 7)
+    st = OR.A10State(total, seeds0)
+    oracle_lib.a10_initAcu(st.acu, total)
+    d_rays, d_pois, d_shadow = ctx.alloc(48 * total), ctx.alloc(64 * total), ctx.alloc(48 * total)
+    d_acu, d_seeds = ctx.alloc(16 * total), ctx.upload(seeds0)
+    ctx.call("rt_buffer_fill", d_rays, 0, 48 * total)
+    ctx.call("rt_buffer_fill", d_pois, 0, 64 * total)
+    ctx.call("rt_buffer_fill", d_shadow, 0, 48 * total)
+    ctx.call("rt_a10_initAcu", d_acu, total)
+    cam = o_scene["camera"].toFloat32Array()
+    focal = float(np.float32(o_scene["focal_length"]))
+    lens = float(np.float32(o_scene["lens_diameter"] / 2.0))
+    report = []
+
+    def compare(tag):
+        rays = ctx.download(d_rays, OR.RAY, total)
+        pois = ctx.download(d_pois, OR.POI10, total)
+        shadow = ctx.download(d_shadow, OR.RAY, total)
+        acu = ctx.download(d_acu, np.float32, total * 4).reshape(-1, 4)
+        seeds = ctx.download(d_seeds, np.int32, total)
+        assert np.array_equal(seeds, st.seeds), tag + ": seed state differs (RNG draw count/order)"
+        live = st.rays["mint"] != st.rays["maxt"]
+        assert np.array_equal(live, rays["mint"] != rays["maxt"]), tag + ": live-ray sets differ"
+        worst = 0
+        for name, a, b in (("ray.o", rays["o"][live, :3], st.rays["o"][live, :3]), ("ray.d", rays["d"][live, :3], st.rays["d"][live, :3]),
+                           ("ray.mint", rays["mint"], st.rays["mint"]), ("ray.maxt", rays["maxt"], st.rays["maxt"])):
+            worst = max(worst, int(util.ulp_diff(a, b).max(initial=0)))
+        hit = st.pois["matId"] >= 0
+        assert np.array_equal(pois["matId"], st.pois["matId"]), tag + ": matId differs"
+        for f in ("p", "normal", "atte"):
+            worst = max(worst, int(util.ulp_diff(pois[f][hit, :3], st.pois[f][hit, :3]).max(initial=0)))
+        slive = st.shadow["mint"] != st.shadow["maxt"]
+        assert np.array_equal(slive, shadow["mint"] != shadow["maxt"]), tag + ": lit/blocked sets differ"
+        worst = max(worst, int(util.ulp_diff(shadow["d"][slive, :3], st.shadow["d"][slive, :3]).max(initial=0)))
+        worst = max(worst, int(util.ulp_diff(acu, st.acu).max(initial=0)))
+        report.append((tag, worst))
+        assert worst == 0, "%s: max ulp distance %d (expected bit-exact)" % (tag, worst)
+
+    def closest(tag):
+        for s, d in zip(prep["sets"], dev["sets"]):
+            if s["kind"] == "sphere":
+                oracle_lib.a10_sphereTrace(total, st.pois, st.rays, s["data"], s["matid"], s["box"], s["aabb"], s["n"])
+                ctx.call("rt_a10_sphereTrace", total, d_pois, d_rays, d["data"], d["matid"], d["box"], _hp(s["aabb"]), s["n"])
+            elif s["kind"] == "triangle":
+                oracle_lib.a10_triangleTrace(total, st.pois, st.rays, s["pos"], s["normal"], s["matid"], s["box"], s["aabb"], s["n"])
+                ctx.call("rt_a10_triangleTrace", total, d_pois, d_rays, d["pos"], d["normal"], d["matid"], d["box"], _hp(s["aabb"]), s["n"])
+            else:
+                oracle_lib.a10_meshTrace(total, st.pois, st.rays, s["pos"], s["normal"], s["box"], s["matid"], s["aabb"], s["n"])
+                ctx.call("rt_a10_meshTrace", total, d_pois, d_rays, d["pos"], d["normal"], d["box"], s["matid"], _hp(s["aabb"]), s["n"])
+            compare(tag + ":" + s["kind"])
+
+    def shade(tag):
+        for li, L in enumerate(prep["lights"]):
+            oracle_lib.a10_initShadowTrace(st.shadow, st.pois, total, L["shadow"], st.seeds)
+            ctx.call("rt_a10_initShadowTrace", d_shadow, d_pois, total, _hp(L["shadow"]), d_seeds)
+            compare("%s:initShadow%d" % (tag, li))
+            for s, d in zip(prep["sets"], dev["sets"]):
+                if s["kind"] == "sphere":
+                    oracle_lib.a10_sphereShadowTrace(total, st.shadow, s["data"], s["box"], s["aabb"], s["n"])
+                    ctx.call("rt_a10_sphereShadowTrace", total, d_shadow, d["data"], d["box"], _hp(s["aabb"]), s["n"])
+                else:
+                    oracle_lib.a10_triangleShadowTrace(total, st.shadow, s["pos"], s["box"], s["aabb"], s["n"])
+                    ctx.call("rt_a10_triangleShadowTrace", total, d_shadow, d["pos"], d["box"], _hp(s["aabb"]), s["n"])
+            oracle_lib.a10_sceneRender(st.acu, st.pois, st.shadow, prep["materials"], L["scene"], total)
+            ctx.call("rt_a10_sceneRender", d_acu, d_pois, d_shadow, dev["materials"], _hp(L["scene"]), total)
+            compare("%s:sceneRender%d" % (tag, li))
+
+    oracle_lib.a10_initTrace(st.seeds, st.rays, st.pois, prep["aabb"], cam, focal, lens, RPP, COLS, ROWS, 0)
+    ctx.call("rt_a10_initTrace", d_seeds, d_rays, d_pois, _hp(prep["aabb"]), _hp(cam), focal, lens, RPP)
+    compare("initTrace")
+    closest("primary")
+    for li, L in enumerate(prep["lights"]):
+        oracle_lib.a10_lightRender(st.pois, st.rays, st.acu, L["light"], total)
+        ctx.call("rt_a10_lightRender", d_pois, d_rays, d_acu, _hp(L["light"]), total)
+        compare("lightRender%d" % li)
+    shade("primary")
+    for j in range(5):
+        oracle_lib.a10_bouncePaths(st.pois, st.rays, st.seeds, total)
+        ctx.call("rt_a10_bouncePaths", d_pois, d_rays, d_seeds, total)
+        compare("bounce%d" % j)
+        closest("bounce%d" % j)
+        shade("bounce%d" % j)
+    pix_o = np.zeros((COLS * ROWS, 4), np.uint8)
+    oracle_lib.a10_copyToPixel(pix_o, st.acu, 1.0 / RPP, COLS * ROWS, RPP)
+    d_pix = ctx.alloc(4 * COLS * ROWS)
+    ctx.call("rt_a10_copyToPixel", d_pix, d_acu, 1.0 / RPP, COLS * ROWS, RPP)
+    pix = ctx.download(d_pix, np.uint8, 4 * COLS * ROWS).reshape(-1, 4)
+    assert np.array_equal(pix, pix_o)
+    assert pix[:, :3].max() > 30, "image is not trivially black"
+
+
+@pytest.mark.parametrize("mode", [1, 0])
+def test_render_frame_matches_oracle(rt, oracle_lib, scenes, mode):
+    """rt_render_execute (mode 1 = reference schedule, mode 0 = fused wavefront path) vs the
+    oracle's executeRender: per-pixel float accumulation within 1e-3 (BASELINE.md gate 4; in
+    practice bit-exact), seed buffer equal as integers, two progressive passes."""
+    o_scene, p_scene = scenes
+    total = COLS * ROWS * RPP
+    seeds0 = OR.make_seeds(total, 11)
+    prep = OR.prepare_a10(o_scene, 1)
+    st = OR.A10State(total, seeds0)
+    oracle_lib.a10_initAcu(st.acu, total)
+    cam = o_scene["camera"].toFloat32Array()
+    r = rt.Renderer(p_scene, COLS, ROWS, RPP, mode=mode, tile_slots=COLS * 8 * RPP)
+    r.preRender(seeds0)
+    try:
+        for p in range(2):
+            pix_o = OR.a10_execute_render(oracle_lib, st, prep, cam, COLS, ROWS, RPP, o_scene["focal_length"], o_scene["lens_diameter"])
+            pix = r.executeRender()
+            acc = r.accum()
+            acc_o = st.acu.reshape(COLS * ROWS, RPP, 4)
+            ref = np.zeros((COLS * ROWS, 4), np.float32)
+            for k in range(RPP):
+                ref += acc_o[:, k]
+            scale = 1.0 / (RPP * (p + 1))
+            assert np.abs(acc[:, :3] - ref[:, :3]).max() * scale <= 1e-3
+            assert np.array_equal(r.seeds(), st.seeds)
+            assert np.array_equal(acc.view(np.uint32), ref.view(np.uint32)), "expected bit-exact accumulation"
+            assert np.array_equal(pix.reshape(-1, 4), pix_o.reshape(-1, 4))
+            s = r.stats()
+            assert s["launches"] > 0
+        assert r.stats()["closest_rays"] + r.stats()["any_rays"] > 0
+        assert st.n_closest + st.n_any > 0
+    finally:
+        r.postRender()
