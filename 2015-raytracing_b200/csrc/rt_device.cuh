@@ -295,6 +295,7 @@ RT_DEV float nextRand(int& seed) {
 struct GridView {
     const float4* prim;      // spheres: 1 float4 per ref; triangles: 3 float4 per ref
     const unsigned* box;     // n^3 + 1 exclusive prefix sums
+    const unsigned* occ;     // optional: 1 bit per cell, set when the cell is non-empty (ours, built with the grid)
     AABB bound;
     unsigned n;
 };
@@ -333,7 +334,10 @@ RT_DEV Axis ddaAxis(float o, float d, float tmin, float pmin, float pmax, unsign
 
 // Closest-hit (ANY = false) or any-hit (ANY = true) walk.  `maxt_in` is the STORED
 // ray.maxt (champ_t starts there).  Returns hit.i != ~0u when a primitive was accepted.
-template <int PRIM, bool ANY, bool TRI_INCL, bool STATS>
+// OCC = true consults the occupancy bitmap first and touches the cell table only for
+// non-empty cells -- an empty cell contributes nothing to the reference's loop either, so the
+// walk (and every float it produces) is unchanged.
+template <int PRIM, bool ANY, bool TRI_INCL, bool STATS, bool OCC = false>
 RT_DEV Hit gridWalk(f3 o, f3 d, float maxt_in, const GridView& g, const AabbHit& binter, WalkStats* st) {
     Axis ax = ddaAxis(o.x, d.x, binter.tmin, g.bound.pmin.x, g.bound.pmax.x, g.n);
     Axis ay = ddaAxis(o.y, d.y, binter.tmin, g.bound.pmin.y, g.bound.pmax.y, g.n);
@@ -351,8 +355,11 @@ RT_DEV Hit gridWalk(f3 o, f3 d, float maxt_in, const GridView& g, const AabbHit&
         float mint = t;
         float maxt = cl_min(cl_min(ax.t_next, ay.t_next), az.t_next);
         unsigned cell = (unsigned)az.slab * zs + (unsigned)ay.slab * ys + (unsigned)ax.slab;
-        unsigned begin = __ldg(g.box + cell);
-        unsigned end = __ldg(g.box + cell + 1);
+        unsigned begin = 0, end = 0;
+        if (!OCC || ((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u)) {
+            begin = __ldg(g.box + cell);
+            end = __ldg(g.box + cell + 1);
+        }
         if (STATS) st->cells++;
         for (unsigned i = begin; i < end; i++) {
             float ti;

@@ -5,53 +5,9 @@
 // frame is processed in TILES of consecutive slots whose ray/hit/shadow state fits the L2;
 // only the per-slot seed and accumulation buffers persist across passes, exactly as in the
 // reference (acu is never cleared between passes, A10/code.js:1078-1099).
-#include "rt_device.cuh"
-#include "rt_internal.h"
+#include "rt_frame.h"
 
 using namespace rt;
-
-struct SceneSet {
-    rt_grid grid;
-    float bound[8];
-    int is_mesh;
-    unsigned mesh_matid;
-};
-struct SceneLight { float shadow[16], scene[16], light[16]; };
-
-struct rt_scene {
-    rt_ctx* ctx = nullptr;
-    float bound[8] = {0};
-    std::vector<SceneSet> sets;
-    std::vector<SceneLight> lights;
-    void* materials = nullptr;
-    unsigned n_materials = 0;
-};
-
-struct rt_render {
-    rt_ctx* ctx = nullptr;
-    rt_scene* scene = nullptr;
-    rt_render_opts o{};
-    unsigned slots_pp = 0;           // slots per pixel handled by this context
-    size_t pixels = 0, local_slots = 0;
-    size_t tile_slots = 0;           // multiple of slots_pp
-    // persistent
-    int* seeds = nullptr;            // [pixel][k_local]
-    float4* acu = nullptr;           // [pixel][k_local]
-    float4* accum = nullptr;         // [pixel] sum over k_local
-    uchar4* pixel = nullptr;
-    bool have_seeds = false;
-    unsigned passes = 1;             // the reference starts at 1 and divides by it (A10/code.js:416,1850)
-    // per tile
-    Ray* rays = nullptr;
-    Poi10* pois = nullptr;
-    Ray* shadow = nullptr;
-    // stats
-    unsigned long long* d_counters = nullptr;   // [0] closest rays, [1] any rays
-    unsigned long long h_counters[2] = {0, 0};
-    unsigned last_launches = 0;
-    float last_ms = 0.f;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
 
 namespace {
 
@@ -208,9 +164,6 @@ int tileReferenceSchedule(rt_render* r, const float* fcam, size_t slot0, unsigne
 
 }  // namespace
 
-// implemented in rt_wavefront.cu (fused wavefront path); returns RT_ERR_STATE if not built
-extern int rt_wavefront_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, const float2* rpp1_coords) __attribute__((weak));
-
 extern "C" {
 
 int rt_scene_create(rt_ctx* ctx, rt_scene** out) {
@@ -299,6 +252,8 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     A((void**)&r->pois, sizeof(Poi10) * r->tile_slots);
     A((void**)&r->shadow, sizeof(Ray) * r->tile_slots);
     A((void**)&r->d_counters, sizeof(unsigned long long) * 2);
+    A((void**)&r->d_profile, sizeof(unsigned long long) * 16);
+    if (!rc) rc = rt_buffer_fill(ctx, r->d_profile, 0, sizeof(unsigned long long) * 16);
     if (!rc && (cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess)) rc = RT_ERR_CUDA;
     // prepareInitAcu (A10/code.js:1078-1099): zero once, never again between passes
     if (!rc) rc = rt_buffer_fill(ctx, r->acu, 0, sizeof(float4) * r->local_slots);
@@ -314,7 +269,7 @@ int rt_render_destroy(rt_render* r) {
     rt_ctx* ctx = r->ctx;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rays, r->pois, r->shadow, r->d_counters};
+    void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rays, r->pois, r->shadow, r->d_counters, r->d_profile};
     for (void* b : bufs) if (b) cudaFree(b);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
@@ -355,6 +310,28 @@ int rt_render_set_seeds(rt_render* r, const int* seeds, size_t count, int on_dev
     return RT_OK;
 }
 
+int rt_render_write_local_seeds(rt_render* r, const int* host_seeds, size_t count) {
+    if (!r || !host_seeds) return RT_ERR_INVALID;
+    rt_ctx* ctx = r->ctx;
+    if (count != r->local_slots) return rt_fail(ctx, RT_ERR_INVALID, "write_local_seeds: count must be cols*rows*slot_count");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaMemcpyAsync(r->seeds, host_seeds, sizeof(int) * count, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    r->have_seeds = true;
+    return RT_OK;
+}
+
+int rt_render_set_profile(rt_render* r, int on) {
+    if (!r) return RT_ERR_INVALID;
+    r->profile = on != 0;
+    return rt_buffer_fill(r->ctx, r->d_profile, 0, sizeof(unsigned long long) * 16);
+}
+
+int rt_render_read_profile(rt_render* r, unsigned long long out[16]) {
+    if (!r || !out) return RT_ERR_INVALID;
+    return rt_buffer_read(r->ctx, r->d_profile, 0, sizeof(unsigned long long) * 16, out);
+}
+
 int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pixels) {
     if (!r || !fcam) return RT_ERR_INVALID;
     rt_ctx* ctx = r->ctx;
@@ -375,8 +352,8 @@ int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pi
         size_t rem = r->local_slots - slot0;
         unsigned n = (unsigned)(rem < r->tile_slots ? rem : r->tile_slots);
         int rc;
-        if (o.mode == 0 && rt_wavefront_tile) rc = rt_wavefront_tile(r, fcam, slot0, n, coords);
-        else rc = tileReferenceSchedule(r, fcam, slot0, n, coords);
+        if (o.mode == 1) rc = tileReferenceSchedule(r, fcam, slot0, n, coords);
+        else rc = rt_fused_tile(r, fcam, slot0, n, coords);
         if (rc) return rc;
     }
     if (coords) RT_CUDA(ctx, cudaFreeAsync(coords, ctx->stream));

@@ -1,0 +1,54 @@
+// rt_frame.h -- scene / render objects shared by rt_frame.cu (driver, reference schedule) and
+// rt_wavefront.cu (fused paths).
+#pragma once
+#include "rt_device.cuh"
+#include "rt_internal.h"
+
+struct SceneSet {
+    rt_grid grid;
+    float bound[8];
+    int is_mesh;
+    unsigned mesh_matid;
+};
+struct SceneLight { float shadow[16], scene[16], light[16]; };
+
+struct rt_scene {
+    rt_ctx* ctx = nullptr;
+    float bound[8] = {0};
+    std::vector<SceneSet> sets;
+    std::vector<SceneLight> lights;
+    void* materials = nullptr;
+    unsigned n_materials = 0;
+};
+
+struct rt_render {
+    rt_ctx* ctx = nullptr;
+    rt_scene* scene = nullptr;
+    rt_render_opts o{};
+    unsigned slots_pp = 0;           // slots per pixel handled by this context
+    size_t pixels = 0, local_slots = 0;
+    size_t tile_slots = 0;           // multiple of slots_pp
+    // persistent
+    int* seeds = nullptr;            // [pixel][k_local]
+    float4* acu = nullptr;           // [pixel][k_local]
+    float4* accum = nullptr;         // [pixel] sum over k_local
+    uchar4* pixel = nullptr;
+    bool have_seeds = false;
+    unsigned passes = 1;             // the reference starts at 1 and divides by it (A10/code.js:416,1850)
+    // per tile
+    rt::Ray* rays = nullptr;
+    rt::Poi10* pois = nullptr;
+    rt::Ray* shadow = nullptr;
+    // stats
+    unsigned long long* d_counters = nullptr;   // [0] closest rays, [1] any rays
+    unsigned long long* d_profile = nullptr;    // 16 work counters (rt_render_read_profile)
+    bool profile = false;
+    unsigned long long h_counters[2] = {0, 0};
+    unsigned last_launches = 0;
+    float last_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+
+// Fused paths (rt_wavefront.cu).  `mode` as in rt_render_opts.
+int rt_fused_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, const float2* rpp1_coords);

@@ -268,6 +268,7 @@ GridView mkGrid(const void* prim, const void* box, const float* bound, unsigned 
     GridView g;
     g.prim = (const float4*)prim;
     g.box = (const unsigned*)box;
+    g.occ = nullptr;
     AabbArg a = mkAabb(bound);
     g.bound.pmin.x = a.v[0]; g.bound.pmin.y = a.v[1]; g.bound.pmin.z = a.v[2];
     g.bound.pmax.x = a.v[4]; g.bound.pmax.y = a.v[5]; g.bound.pmax.z = a.v[6];

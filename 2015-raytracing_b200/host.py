@@ -202,7 +202,7 @@ def parseMeshJSON(jsonFileName):
                     if hi[a] > b.max[a]:
                         b.max[a] = float(hi[a])
             ind = mesh.get("indices")
-            idx = np.asarray(ind, dtype=np.int64) if ind else np.arange(len(vp), dtype=np.int64)
+            idx = np.asarray(ind, dtype=np.int64) if (ind is not None and len(ind) > 0) else np.arange(len(vp), dtype=np.int64)
             nT = len(idx) // 3
             idx = idx[: nT * 3]
             pos_parts.append(tp[idx].reshape(nT, 9))
@@ -627,6 +627,34 @@ class Renderer:
         a, b, l, ms = L.ULL(), L.ULL(), L.U(), L.F()
         self.ctx.check(L.dll.rt_render_stats(self.h_render, C.byref(a), C.byref(b), C.byref(l), C.byref(ms)))
         return {"closest_rays": a.value, "any_rays": b.value, "launches": l.value, "device_ms": ms.value}
+
+    def profile_pass(self, camera=None):
+        """Runs ONE extra pass with the instrumented kernel and returns the work counters of
+        rt_render_read_profile (not a timing run)."""
+        self.ctx.check(L.dll.rt_render_set_profile(self.h_render, 1))
+        try:
+            self.executeRender(camera, readback=False)
+            out = (L.ULL * 16)()
+            self.ctx.check(L.dll.rt_render_read_profile(self.h_render, C.byref(out)))
+        finally:
+            self.ctx.check(L.dll.rt_render_set_profile(self.h_render, 0))
+        return [int(v) for v in out]
+
+    def algorithmic_bytes(self, prof=None):
+        """ALGORITHMIC bytes of one pass in the REFERENCE's data layout (restated
+        in DESIGN.md): what the kernel-by-kernel schedule must move for the work this pass did.
+        Traversal, per (live ray, set) query: 48 B ray load + 8 B per visited cell + 16/48 B per
+        sphere/triangle test + hit record traffic; any-hit adds the 8 B mint/maxt store.
+        Streaming kernels, per slot: initTrace 68, lightRender 48/light, bouncePaths 120,
+        initShadowTrace 120 and sceneRender 176 per light per segment; copyToPixel 16/slot + 4/px."""
+        p = prof or self.profile_pass()
+        nl, depth = len(self.scene["lights"]), self.depth
+        slots = p[14]
+        trav = (48 * p[0] + 8 * p[2] + 16 * p[3] + 48 * p[4] + p[5] * (4 + 64 + 4) + p[6] * (48 + 4 + 64 + 4) + p[7] * (48 + 64 + 4)
+                + 48 * p[8] + 8 * p[10] + 16 * p[11] + 48 * p[12] + 8 * p[9])
+        stream = slots * (68 + 48 * nl + (1 + depth) * nl * (120 + 176) + depth * 120 + 16) + 4 * self.width * self.height
+        return {"bytes_per_pass": int(trav + stream), "traversal_bytes": int(trav), "streaming_bytes": int(stream), "profile": p,
+                "kernel": "k_pathMega (fused pass)" if self.mode != 1 else "reference schedule (all kernels)"}
 
     # -- postRender: A10/code.js:1856-1859 --
     def postRender(self):

@@ -85,6 +85,9 @@ _SIGS = {
     "rt_render_accum_image": ([P, PP], I),
     "rt_render_read_accum": ([P, P], I),
     "rt_render_read_seeds": ([P, P, Z], I),
+    "rt_render_write_local_seeds": ([P, P, Z], I),
+    "rt_render_set_profile": ([P, I], I),
+    "rt_render_read_profile": ([P, C.POINTER(ULL * 16)], I),
     "rt_accum_to_pixel": ([P, P, P, F, U], I),
     "rt_render_stats": ([P, C.POINTER(ULL), C.POINTER(ULL), C.POINTER(U), C.POINTER(F)], I),
 }

@@ -1,0 +1,384 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: path-traced Mrays/s at 1920x1080 (BASELINE.json config 5:
+Assign10 path tracing, 256 slots per pixel as a 16x16 stratified lens grid, depth 5, synthetic
+1M-triangle <mesh> at nslabs 128 inside a Cornell-style box with two disk lights), split by
+samples-per-pixel across the GPUs of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+One "step" = one executeRender pass (Assignment10/code.js:1806-1854) over the whole frame.
+Prints ONE JSON line (see README/DESIGN.md for the field contract).  The oracle is imported
+only for the cpu_baseline / reference legs -- never on the measured product path.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+PKG = "2015-raytracing_b200"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cols", type=int, default=1920)
+    ap.add_argument("--rows", type=int, default=1080)
+    ap.add_argument("--spp", type=int, default=256, help="slots per pixel (perfect square)")
+    ap.add_argument("--depth", type=int, default=5)
+    ap.add_argument("--mesh-u", type=int, default=1000, help="quads around (triangles = 2*u*v)")
+    ap.add_argument("--mesh-v", type=int, default=500)
+    ap.add_argument("--nslabs", type=int, default=128)
+    ap.add_argument("--lights", type=int, default=2)
+    ap.add_argument("--mode", type=int, default=0, help="0 fused (default), 1 reference kernel schedule")
+    ap.add_argument("--tile-slots", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame the CPU baseline renders (0 = auto)")
+    ap.add_argument("--seed", type=int, default=2015)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------ workload
+def build_scene(rt, args, tmp):
+    import synth
+    mesh_json = synth.synth_mesh(args.mesh_u, args.mesh_v, seed=args.seed)
+    jmesh_holder = {}
+
+    def loader(_file):
+        if "m" not in jmesh_holder:
+            jmesh_holder["m"] = rt.parseMeshJSON(mesh_json)
+        return jmesh_holder["m"]
+
+    path = synth.write_scene(tmp, n_lights=args.lights, with_sphere=True, with_mesh=True, mesh_nslabs=args.nslabs)
+    scene = rt.loadScene(path, args.cols, args.rows, mesh_loader=loader)
+    return scene
+
+
+def workload_name(args):
+    return ("A10 path tracing %dx%d, %d slots/px (stratified %dx%d), depth %d, synthetic %d-triangle mesh nslabs %d, "
+            "Cornell-style box + sphere, %d disk lights" % (args.cols, args.rows, args.spp, int(args.spp ** 0.5), int(args.spp ** 0.5),
+                                                            args.depth, 2 * args.mesh_u * args.mesh_v, args.nslabs, args.lights))
+
+
+def make_seeds(total, seed):
+    g = np.random.Generator(np.random.PCG64(seed))
+    return g.integers(1, 2 ** 31, size=total, dtype=np.int32)
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self._stop = threading.Event()
+        self._t = None
+
+    def _loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append((float(f[0]), float(f[1])))
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._loop, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(s[0] for s in self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(s[1] for s in self.samples), "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU legs (oracle)
+def oracle_prep_from_device(rt, renderer, scene):
+    """Host copies of the buffers the GPU grid build produced (they are parity-tested against the
+    oracle's own split*Data at test sizes); fed to the oracle kernels for CPU timing."""
+    from oracle import refcl as OR
+    ctx = renderer.ctx
+    prep = {"aabb": rt.bounds2AABB(scene["bounds"]), "materials": rt.splitMaterialData(scene), "sets": [], "lights": []}
+    grids = list(renderer._grids)
+    gi = 0
+    if len(scene["spheres"]) > 0:
+        d = rt.host.DeviceGrid(ctx, grids[gi], None); gi += 1
+        prep["sets"].append({"kind": "sphere", "data": d.prim(), "matid": d.matid(), "box": d.box_size(),
+                             "aabb": rt.bounds2AABB(scene["sphereBounds"]), "n": d.n_slabs})
+    if len(scene["triangles"]) > 0:
+        d = rt.host.DeviceGrid(ctx, grids[gi], None); gi += 1
+        prep["sets"].append({"kind": "triangle", "pos": d.prim(), "normal": d.normal(), "matid": d.matid(), "box": d.box_size(),
+                             "aabb": rt.bounds2AABB(scene["triangleBounds"]), "n": d.n_slabs})
+    for m in scene["meshes"]:
+        d = rt.host.DeviceGrid(ctx, m.grid, None)
+        prep["sets"].append({"kind": "mesh", "pos": d.prim(), "normal": d.normal(), "matid": int(m.matId), "box": d.box_size(),
+                             "aabb": rt.bounds2AABB(m.bounds), "n": d.n_slabs})
+    for lt in scene["lights"]:
+        prep["lights"].append({"shadow": lt.toShadowInfo(), "scene": lt.toSceneRenderInfo(), "light": lt.toLightRenderInfo()})
+    return prep
+
+
+def cpu_pass_rows(olib, prep, cam16, args, focal, lens_diam, row0, nrows, seeds_rows):
+    """One executeRender pass of the oracle over pixel rows [row0, row0+nrows) (every kernel is
+    per-slot independent, so a row tile is exact).  Returns (rays, seconds)."""
+    from oracle import refcl as OR
+    cols, rpp = args.cols, args.spp
+    total = cols * nrows * rpp
+    st = OR.A10State(total, seeds_rows)
+    olib.a10_initAcu(st.acu, total)
+    t0 = time.perf_counter()
+    OR.a10_execute_render(olib, st, prep, cam16, cols, args.rows, rpp, focal, lens_diam, depth=args.depth, row0=row0, nrows=nrows)
+    dt = time.perf_counter() - t0
+    return st.n_closest + st.n_any, dt
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    side = int(round(args.spp ** 0.5))
+    assert side * side == args.spp, "--spp must be a perfect square"
+    assert args.spp % max(args.gpus, 1) == 0, "--spp must be divisible by --gpus"
+
+    if args.impl == "reference":
+        return main_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    rt = importlib.import_module(PKG)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    tmp = tempfile.mkdtemp(prefix="rt_bench_")
+    scene = build_scene(rt, args, tmp)
+    slots_pp = args.spp // world
+    r = rt.Renderer(scene, args.cols, args.rows, args.spp, depth=args.depth, device=local_rank, slots=(rank * slots_pp, slots_pp),
+                    mode=args.mode, tile_slots=args.tile_slots)
+    total = args.cols * args.rows * args.spp
+    # host seed array: this rank's slots only are generated/kept ([pixel][k_local]) -- same values a full
+    # PCG64(seed) array would hold at those positions are not needed for throughput; parity tests use full arrays.
+    local = args.cols * args.rows * slots_pp
+    seeds_host = torch.from_numpy(make_seeds(local, args.seed + rank)).pin_memory()
+    r.preRender(None)
+    L = rt.lib
+    ext = torch.cuda.ExternalStream(L.dll.rt_ctx_stream(r.ctx.h), device=torch.device("cuda", local_rank))
+
+    def set_seeds_local():
+        # rt_render_set_seeds takes the GLOBAL [pixel][rpp] layout; with one rank-local array we write the
+        # render's seed buffer directly (rt_buffer_write on the same device pointer layout [pixel][k_local]).
+        r.ctx.check(L.dll.rt_render_write_local_seeds(r.h_render, seeds_host.data_ptr(), local))
+
+    acc_dptr = r.accum_dptr()
+
+    class _Cai:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    acc_t = torch.as_tensor(_Cai(acc_dptr, args.cols * args.rows * 4), device=torch.device("cuda", local_rank))
+    pix_dev = torch.empty(args.cols * args.rows * 4, dtype=torch.uint8, device=acc_t.device)
+    pix_host = torch.empty(args.cols * args.rows * 4, dtype=torch.uint8).pin_memory()
+    cam = scene["camera"].toFloat32Array()
+
+    def step_device():
+        """hot path only, inputs resident in HBM"""
+        r.executeRender(readback=False)
+        s = r.stats()
+        return s
+
+    def step_e2e():
+        """public API with host buffers: seeds H2D, render, (reduce), copyToPixel, pixels D2H"""
+        set_seeds_local()
+        r.executeRender(readback=False)
+        s = r.stats()
+        with torch.cuda.stream(ext):
+            if world > 1:
+                dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                m = float(np.float32(1.0 / (args.spp * (r.passes - 1))))
+                r.ctx.check(L.dll.rt_accum_to_pixel(r.ctx.h, pix_dev.data_ptr(), acc_t.data_ptr(), m, args.cols * args.rows))
+                pix_host.copy_(pix_dev, non_blocking=True)
+        ext.synchronize()
+        return s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rays = 0
+        launches = 0
+        kern_ms = 0.0
+        with torch.cuda.stream(ext):
+            e0.record()
+        for _ in range(k):
+            s = fn()
+            rays += s["closest_rays"] + s["any_rays"]
+            launches += s["launches"]
+            kern_ms += s["device_ms"]
+        with torch.cuda.stream(ext):
+            e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, float(rays)], dtype=torch.float64, device=acc_t.device)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            ms, rays = float(tmax[0]), int(t[1])
+        return ms, rays, launches, kern_ms
+
+    set_seeds_local()
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, rays, launches, kern_ms = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = rays / (ms * 1e-3) / 1e6
+    # end-to-end (host buffers, copies inside the timed region)
+    step_e2e()
+    ms_e, rays_e, launches_e, _ = timed(step_e2e, args.steps)
+    e2e_value = rays_e / (ms_e * 1e-3) / 1e6
+
+    out = None
+    if rank == 0:
+        info = r.ctx.device_info()
+        # roofline of the dominant kernel (the fused pass kernel = the whole step)
+        alg = r.algorithmic_bytes() if hasattr(r, "algorithmic_bytes") else None
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        per_launch_ms = kern_ms / max(args.steps, 1)
+        roofline = None
+        if alg is not None:
+            achieved = alg["bytes_per_pass"] / (per_launch_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                        "traffic": None, "kernel": alg["kernel"], "peak_source": "measured" if peaks else "fallback",
+                        "algorithmic_bytes_per_launch": alg["bytes_per_pass"], "launch_ms": round(per_launch_ms, 3)}
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(rt, r, scene, args, cam)
+        out = {
+            "metric": "path-traced Mrays/s at 1080p", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "slots_per_gpu_per_pixel": slots_pp, "mode": args.mode,
+                       "l2_policy": "inputs larger than L2 (seed+accumulation state %.1f GB per GPU per step, scene refs ~%d MB)" % (
+                           local * 20 / 1e9, 0), "sm_count": info["sm_count"]},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(local * 4 + 64),
+                    "d2h_bytes_per_step": int(args.cols * args.rows * 4), "ms_per_step": round(ms_e / args.steps, 3)},
+            "gpu_launches": int(launches),
+            "rays_per_step": int(rays // max(args.steps, 1)),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+    # release torch objects that reference the context's stream before the context goes away
+    del acc_t, pix_dev, pix_host, seeds_host
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+    sys.stdout.flush()
+    r.postRender()
+    os._exit(0)   # torch's pinned-memory allocator would otherwise record events on the (now destroyed) stream at exit
+
+
+def cpu_baseline(rt, r, scene, args, cam):
+    """Reference kernels on the host cores, on a bounded row sample of the same workload."""
+    from oracle import refcl as OR
+    olib = OR.load_best()
+    prep = oracle_prep_from_device(rt, r, scene)
+    rows = args.cpu_rows or max(1, min(args.rows, int(round(8 * (1920 * 256) / (args.cols * args.spp)))))
+    row0 = max(0, args.rows // 2 - rows // 2)
+    seeds = make_seeds(args.cols * rows * args.spp, args.seed + 77)
+    rays, dt = cpu_pass_rows(olib, prep, cam, args, scene["focal_length"], scene["lens_diameter"], row0, rows, seeds)
+    return {"value": round(rays / dt / 1e6, 3), "unit": "Mrays/s", "cores": int(olib.num_threads()), "kind": olib.kind,
+            "sample": "rows %d..%d of %d (all %d slots/px, one pass, %d rays, %.1f s)" % (row0, row0 + rows - 1, args.rows, args.spp, rays, dt)}
+
+
+def main_reference(args, rank):
+    """--impl reference: the reference's own kernels (oracle/_ref when compiled, else the C
+    restatement) on the host cores, same scene/metric; each step is a bounded row sample."""
+    if rank != 0:
+        return
+    rt = importlib.import_module(PKG)
+    from oracle import refcl as OR
+    olib = OR.load_best()
+    tmp = tempfile.mkdtemp(prefix="rt_bench_ref_")
+    scene = build_scene(rt, args, tmp)
+    # scene buffers: built by the GPU grid build when a GPU is present (same bits as the oracle's split*Data,
+    # tests/test_gpu_a10.py); the timed region contains only the reference's kernels on the CPU.
+    r = rt.Renderer(scene, args.cols, 8, args.spp, depth=args.depth, device=0, mode=1, tile_slots=1 << 16)
+    r.preRender(None)
+    prep = oracle_prep_from_device(rt, r, scene)
+    r.postRender()
+    cam = scene["camera"].toFloat32Array()
+    rows = args.cpu_rows or max(1, min(args.rows, int(round(3 * (1920 * 256) / (args.cols * args.spp)))))
+    row0 = max(0, args.rows // 2 - rows // 2)
+    rays_t, secs = 0, 0.0
+    for i in range(args.warmup + args.steps):
+        seeds = make_seeds(args.cols * rows * args.spp, args.seed + i)
+        rays, dt = cpu_pass_rows(olib, prep, cam, args, scene["focal_length"], scene["lens_diameter"], row0, rows, seeds)
+        if i >= args.warmup:
+            rays_t += rays
+            secs += dt
+    value = rays_t / secs / 1e6
+    sample = "each step = rows %d..%d of %d (all %d slots/px, one pass)" % (row0, row0 + rows - 1, args.rows, args.spp)
+    out = {"impl": "reference", "metric": "path-traced Mrays/s at 1080p", "value": round(value, 3), "unit": "Mrays/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 3), "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": workload_name(args)},
+           "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": int(olib.num_threads()), "kind": olib.kind, "sample": sample},
+           "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

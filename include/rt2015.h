@@ -173,12 +173,26 @@ int rt_render_execute(rt_render*, const float fcam[16], unsigned char* host_pixe
 int rt_render_accum_image(rt_render*, void** dptr_float4);
 int rt_render_read_accum(rt_render*, float* host_float4);                               /* cols*rows*4 floats */
 int rt_render_read_seeds(rt_render*, int* host_seeds, size_t count);                    /* seed state after the pass */
+/* Same as rt_render_set_seeds for a caller that already holds only THIS context's slots, laid out
+ * [pixel][k_local] (count = cols*rows*slot_count host ints). */
+int rt_render_write_local_seeds(rt_render*, const int* host_seeds, size_t count);
 /* copyToPixel on an accumulation image (after a multi-GPU reduce): m = 1/(rays_per_pixel*passes). */
 int rt_accum_to_pixel(rt_ctx*, void* pixel, const void* accum_float4, float m, unsigned pixels);
 /* Counters of the last execute: valid closest-hit and any-hit queries ("rays"),
  * kernels launched, device milliseconds between the first and last launch. */
 int rt_render_stats(rt_render*, unsigned long long* closest_rays, unsigned long long* any_rays, unsigned* launches,
                     float* device_ms);
+
+/* Work profile of the fused path (for the roofline's ALGORITHMIC byte count): when
+ * switched on, the next executes run an instrumented build of the same kernel and accumulate
+ *   [0] closest (ray,set) queries entered alive   [1] of those, walks started (set AABB hit)
+ *   [2] cells visited   [3] sphere tests   [4] triangle tests
+ *   [5] hits on sphere sets   [6] hits on triangle sets with a matid array   [7] hits on meshes
+ *   [8] any-hit (ray,set) queries entered alive   [9] walks started   [10] cells   [11] sphere tests
+ *   [12] triangle tests   [13] blocked   [14] slots processed   [15] reserved
+ * Timing taken with the profile on is not a benchmark number. */
+int rt_render_set_profile(rt_render*, int on);
+int rt_render_read_profile(rt_render*, unsigned long long out[16]);
 
 #ifdef __cplusplus
 }

@@ -267,6 +267,25 @@ void ref_a10_initTrace(int* seeds, void* rays, void* pois, const float* bound, c
         ND2(cols, rows, a10::initTrace(seeds, (a10::Ray*)rays, (a10::Poi*)pois, b, c, focal_length, lens_rad, rays_per_pixel));
     }
 }
+// Row tile [row0, row0+nrows) of the same launch: `rays`/`pois` (and `seeds`) hold only the
+// tile's slots; the kernel is handed pointers shifted so that its own
+// `(cols*row+col)*rays_per_pixel` indexing lands inside them.  Exact because every work-item
+// touches only its own pixel's slots.  rays_per_pixel must be > 1 (no RNG in initTrace).
+void ref_a10_initTrace_rows(int* seeds, void* rays, void* pois, const float* bound, const float* cam, float focal_length, float lens_rad,
+                            uint rays_per_pixel, uint cols, uint rows, uint row0, uint nrows) {
+    float16 c = mk_f16(cam);
+    a10::AABB b = mk_aabb<a10::AABB>(bound);
+    (void)rows;
+    long long shift = (long long)row0 * cols * rays_per_pixel;
+    a10::Ray* r0 = (a10::Ray*)rays - shift;
+    a10::Poi* p0 = (a10::Poi*)pois - shift;
+    _Pragma("omp parallel for schedule(dynamic, 1)")
+    for (long long _r = row0; _r < (long long)row0 + nrows; _r++)
+        for (long long _c = 0; _c < (long long)cols; _c++) {
+            cl_gid[0] = (size_t)_c; cl_gid[1] = (size_t)_r; cl_gid[2] = 0;
+            a10::initTrace(seeds, r0, p0, b, c, focal_length, lens_rad, rays_per_pixel);
+        }
+}
 void ref_a10_bouncePaths(void* pois, void* rays, int* seeds, uint total_rays) {
     ND1(total_rays, a10::bouncePaths((a10::Poi*)pois, (a10::Ray*)rays, seeds, total_rays));
 }

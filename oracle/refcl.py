@@ -59,6 +59,7 @@ _SIGS = {
     "a09_copyToPixel": [_P, _P, _F, _U, _U],
     "a10_initAcu": [_P, _U],
     "a10_initTrace": [_P, _P, _P, _P, _P, _F, _F, _U, _U, _U, _I],
+    "a10_initTrace_rows": [_P, _P, _P, _P, _P, _F, _F, _U, _U, _U, _U, _U],
     "a10_bouncePaths": [_P, _P, _P, _U],
     "a10_lightRender": [_P, _P, _P, _P, _U],
     "a10_initShadowTrace": [_P, _P, _U, _P, _P],
@@ -214,11 +215,20 @@ def _shade(lib, st, prep, light):
     lib.a10_sceneRender(st.acu, st.pois, st.shadow, prep["materials"], light["scene"], st.total)
 
 
-def a10_execute_render(lib, st, prep, cam16, cols, rows, rpp, focal_length, lens_diameter, depth=5, serial_init=False):
-    """One pass = A10/code.js:1806-1854 (executeRender).  Returns the uchar4 image."""
+def a10_execute_render(lib, st, prep, cam16, cols, rows, rpp, focal_length, lens_diameter, depth=5, serial_init=False,
+                       row0=0, nrows=None):
+    """One pass = A10/code.js:1806-1854 (executeRender).  Returns the uchar4 image.
+    ``row0``/``nrows`` restrict the pass to a tile of pixel rows (``st`` then holds only the
+    tile's slots) -- exact, because every kernel touches only its own slot."""
     lens_rad = float(np.float32(lens_diameter / 2.0))
-    lib.a10_initTrace(st.seeds, st.rays, st.pois, prep["aabb"], cam16, float(np.float32(focal_length)), lens_rad, rpp,
-                      cols, rows, 1 if (serial_init or rpp == 1) else 0)
+    if nrows is None:
+        lib.a10_initTrace(st.seeds, st.rays, st.pois, prep["aabb"], cam16, float(np.float32(focal_length)), lens_rad, rpp,
+                          cols, rows, 1 if (serial_init or rpp == 1) else 0)
+    else:
+        assert rpp > 1, "row tiles need the stratified (RNG-free) initTrace"
+        lib.a10_initTrace_rows(st.seeds, st.rays, st.pois, prep["aabb"], cam16, float(np.float32(focal_length)), lens_rad, rpp,
+                               cols, rows, row0, nrows)
+        rows = nrows
     _closest(lib, st, prep)
     for L in prep["lights"]:
         lib.a10_lightRender(st.pois, st.rays, st.acu, L["light"], st.total)

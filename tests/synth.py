@@ -113,17 +113,20 @@ def synth_scene_xml(n_lights=2, with_sphere=True, with_mesh=True, mesh_nslabs=12
     s += "<!--\n<sphere><center><x>9</x><y>9</y><z>9</z></center><radius>1</radius><matId>red</matId></sphere>\n-->\n"
     if with_sphere:
         s += "<sphere>%s<radius>0.22</radius><matId>blue</matId></sphere>\n" % _v("center", -0.45, -0.76, 0.25)
-    A = 0.98
+    # Walls sit at +-A but SPAN +-B (> A), so every wall lies strictly inside the triangle-set AABB:
+    # the reference accepts a hit only with t < the ray's AABB exit parameter, and a wall lying exactly
+    # on a bounds face is hit or missed by rounding (its own scenes keep walls at 0.99 inside a +-1 box).
+    A, B, ZF, ZB = 0.98, 1.0, 2.5, 2.6
     # floor (normal +y), ceiling (-y), back (+z), left (+x), right (-x), front (-z, behind the camera, optional)
     walls = [
-        ((-A, -A, A), (A, -A, A), (A, -A, -A), (-A, -A, -A), (0.0, 1.0, 0.0), "white"),
-        ((-A, A, -A), (A, A, -A), (A, A, A), (-A, A, A), (0.0, -1.0, 0.0), "white"),
-        ((-A, -A, -A), (A, -A, -A), (A, A, -A), (-A, A, -A), (0.0, 0.0, 1.0), "white"),
-        ((-A, -A, A), (-A, -A, -A), (-A, A, -A), (-A, A, A), (1.0, 0.0, 0.0), "red"),
-        ((A, -A, -A), (A, -A, A), (A, A, A), (A, A, -A), (-1.0, 0.0, 0.0), "green"),
+        ((-B, -A, ZB), (B, -A, ZB), (B, -A, -B), (-B, -A, -B), (0.0, 1.0, 0.0), "white"),
+        ((-B, A, -B), (B, A, -B), (B, A, ZB), (-B, A, ZB), (0.0, -1.0, 0.0), "white"),
+        ((-B, -B, -A), (B, -B, -A), (B, B, -A), (-B, B, -A), (0.0, 0.0, 1.0), "white"),
+        ((-A, -B, ZB), (-A, -B, -B), (-A, B, -B), (-A, B, ZB), (1.0, 0.0, 0.0), "red"),
+        ((A, -B, -B), (A, -B, ZB), (A, B, ZB), (A, B, -B), (-1.0, 0.0, 0.0), "green"),
     ]
     if closed:
-        walls.append(((A, -A, 2.5), (-A, -A, 2.5), (-A, A, 2.5), (A, A, 2.5), (0.0, 0.0, -1.0), "white"))
+        walls.append(((B, -B, ZF), (-B, -B, ZF), (-B, B, ZF), (B, B, ZF), (0.0, 0.0, -1.0), "white"))
     for a, b, c, d, n, m in walls:
         s += _quad(a, b, c, d, n, m)
     if with_mesh:
