@@ -332,77 +332,176 @@ RT_DEV Axis ddaAxis(float o, float d, float tmin, float pmin, float pmax, unsign
     return a;
 }
 
-// Closest-hit (ANY = false) or any-hit (ANY = true) walk.  `maxt_in` is the STORED
-// ray.maxt (champ_t starts there).  Returns hit.i != ~0u when a primitive was accepted.
+// Resumable 3D-DDA walker: the state of the reference's `while(true)` loop (A10/code.cl:745-786)
+// so that the loop can be run either to completion by one thread (gridWalk) or one cell at a
+// time by a persistent warp that refills idle lanes from a queue (rt_wavefront.cu).  Both use
+// walkCell, hence produce identical floats.
+struct Walker {
+    f3 o, d;
+    float a_dd;          // dot(d,d), spheres only
+    Axis ax, ay, az;
+    float t;             // entry parameter of the current cell
+    float tmax_b;        // binter.tmax
+    Hit h;
+};
+
+RT_DEV void walkInit(Walker& w, int prim, f3 o, f3 d, float maxt_in, const GridView& g, const AabbHit& binter) {
+    w.o = o; w.d = d;
+    w.ax = ddaAxis(o.x, d.x, binter.tmin, g.bound.pmin.x, g.bound.pmax.x, g.n);
+    w.ay = ddaAxis(o.y, d.y, binter.tmin, g.bound.pmin.y, g.bound.pmax.y, g.n);
+    w.az = ddaAxis(o.z, d.z, binter.tmin, g.bound.pmin.z, g.bound.pmax.z, g.n);
+    w.h.t = maxt_in;     // champ_t starts at the STORED ray.maxt
+    w.h.i = 0xFFFFFFFFu;
+    w.h.beta = 0.f; w.h.gamma = 0.f;
+    w.h.cx = w.h.cy = w.h.cz = (int)g.n;
+    w.t = binter.tmin;
+    w.tmax_b = binter.tmax;
+    w.a_dd = (prim == PRIM_SPHERE) ? dot(d, d) : 0.f;
+}
+
+// One iteration of the reference loop: test the current cell's references, then advance.
+// Returns true when the walk is over (a hit was accepted in this cell, or the ray left the grid).
 // OCC = true consults the occupancy bitmap first and touches the cell table only for
 // non-empty cells -- an empty cell contributes nothing to the reference's loop either, so the
 // walk (and every float it produces) is unchanged.
-template <int PRIM, bool ANY, bool TRI_INCL, bool STATS, bool OCC = false>
-RT_DEV Hit gridWalk(f3 o, f3 d, float maxt_in, const GridView& g, const AabbHit& binter, WalkStats* st) {
-    Axis ax = ddaAxis(o.x, d.x, binter.tmin, g.bound.pmin.x, g.bound.pmax.x, g.n);
-    Axis ay = ddaAxis(o.y, d.y, binter.tmin, g.bound.pmin.y, g.bound.pmax.y, g.n);
-    Axis az = ddaAxis(o.z, d.z, binter.tmin, g.bound.pmin.z, g.bound.pmax.z, g.n);
-    Hit h;
-    h.t = maxt_in;
-    h.i = 0xFFFFFFFFu;
-    h.beta = 0.f; h.gamma = 0.f;
-    h.cx = h.cy = h.cz = (int)g.n;
-    float t = binter.tmin;
-    const unsigned zs = g.n * g.n, ys = g.n;
-    float a_dd = 0.f;
-    if (PRIM == PRIM_SPHERE) a_dd = dot(d, d);
-    while (true) {
-        float mint = t;
-        float maxt = cl_min(cl_min(ax.t_next, ay.t_next), az.t_next);
-        unsigned cell = (unsigned)az.slab * zs + (unsigned)ay.slab * ys + (unsigned)ax.slab;
-        unsigned begin = 0, end = 0;
-        if (!OCC || ((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u)) {
-            begin = __ldg(g.box + cell);
-            end = __ldg(g.box + cell + 1);
-        }
-        if (STATS) st->cells++;
-        for (unsigned i = begin; i < end; i++) {
-            float ti;
-            bool v;
-            float be = 0.f, ga = 0.f;
-            if (PRIM == PRIM_SPHERE) {
-                float4 s = __ldg(g.prim + i);
-                v = interSphere(o, d, a_dd, mint, maxt, s, ti);
-            } else {
-                float4 q0 = __ldg(g.prim + 3 * i), q1 = __ldg(g.prim + 3 * i + 1), q2 = __ldg(g.prim + 3 * i + 2);
-                v = interTriangle<TRI_INCL>(o, d, mint, maxt, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z),
-                                            mk3(q2.x, q2.y, q2.z), be, ga, ti);
-            }
-            if (STATS) st->tests++;
-            if (v && ti < h.t) {
-                h.t = ti;
-                h.i = i;
-                h.beta = be;
-                h.gamma = ga;
-                h.cx = ax.slab; h.cy = ay.slab; h.cz = az.slab;
-                if (ANY) break;
-            }
-        }
-        if (h.i != 0xFFFFFFFFu) break;
-        t = maxt;
-        if (t == ax.t_next) {
-            ax.t_next += ax.delta_t;
-            if (t >= binter.tmax) break;
-            ax.slab += ax.step;
-            if (ax.slab == ax.limit) break;
-        } else if (t == ay.t_next) {
-            ay.t_next += ay.delta_t;
-            if (t >= binter.tmax) break;
-            ay.slab += ay.step;
-            if (ay.slab == ay.limit) break;
+template <int PRIM, bool ANY, bool TRI_INCL, bool STATS, bool OCC>
+RT_DEV bool walkCell(Walker& w, const GridView& g, WalkStats* st) {
+    float mint = w.t;
+    float maxt = cl_min(cl_min(w.ax.t_next, w.ay.t_next), w.az.t_next);
+    unsigned cell = (unsigned)w.az.slab * (g.n * g.n) + (unsigned)w.ay.slab * g.n + (unsigned)w.ax.slab;
+    unsigned begin = 0, end = 0;
+    if (!OCC || ((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u)) {
+        begin = __ldg(g.box + cell);
+        end = __ldg(g.box + cell + 1);
+    }
+    if (STATS) st->cells++;
+    for (unsigned i = begin; i < end; i++) {
+        float ti;
+        bool v;
+        float be = 0.f, ga = 0.f;
+        if (PRIM == PRIM_SPHERE) {
+            float4 s = __ldg(g.prim + i);
+            v = interSphere(w.o, w.d, w.a_dd, mint, maxt, s, ti);
         } else {
-            az.t_next += az.delta_t;
-            if (t >= binter.tmax) break;
-            az.slab += az.step;
-            if (az.slab == az.limit) break;
+            float4 q0 = __ldg(g.prim + 3 * i), q1 = __ldg(g.prim + 3 * i + 1), q2 = __ldg(g.prim + 3 * i + 2);
+            v = interTriangle<TRI_INCL>(w.o, w.d, mint, maxt, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z),
+                                        mk3(q2.x, q2.y, q2.z), be, ga, ti);
+        }
+        if (STATS) st->tests++;
+        if (v && ti < w.h.t) {
+            w.h.t = ti;
+            w.h.i = i;
+            w.h.beta = be;
+            w.h.gamma = ga;
+            w.h.cx = w.ax.slab; w.h.cy = w.ay.slab; w.h.cz = w.az.slab;
+            if (ANY) break;
         }
     }
-    return h;
+    if (w.h.i != 0xFFFFFFFFu) return true;
+    float t = maxt;
+    w.t = t;
+    if (t == w.ax.t_next) {
+        w.ax.t_next += w.ax.delta_t;
+        if (t >= w.tmax_b) return true;
+        w.ax.slab += w.ax.step;
+        if (w.ax.slab == w.ax.limit) return true;
+    } else if (t == w.ay.t_next) {
+        w.ay.t_next += w.ay.delta_t;
+        if (t >= w.tmax_b) return true;
+        w.ay.slab += w.ay.step;
+        if (w.ay.slab == w.ay.limit) return true;
+    } else {
+        w.az.t_next += w.az.delta_t;
+        if (t >= w.tmax_b) return true;
+        w.az.slab += w.az.step;
+        if (w.az.slab == w.az.limit) return true;
+    }
+    return false;
+}
+
+// ---- flattened form of the same loop, for the queue walkers --------------------------------
+// The unit of work is ONE primitive test or ONE cell change, so that lanes of a warp that sit in
+// cells of very different population (0 .. 100+ references) all make progress every iteration.
+// FlatWalker = Walker + the current cell's [mint,maxt] and reference cursor.
+struct FlatWalker {
+    Walker w;
+    float mint, maxt;     // parameter interval of the current cell
+    unsigned i, end;      // next reference to test, end of the cell's list
+};
+
+// Enter the cell the walker stands in: its parameter interval and reference range
+// (A10/code.cl:747-752; occupancy bitmap first, see walkCell).
+RT_DEV void flatEnter(FlatWalker& f, const GridView& g) {
+    Walker& w = f.w;
+    f.mint = w.t;
+    f.maxt = cl_min(cl_min(w.ax.t_next, w.ay.t_next), w.az.t_next);
+    unsigned cell = (unsigned)w.az.slab * (g.n * g.n) + (unsigned)w.ay.slab * g.n + (unsigned)w.ax.slab;
+    unsigned begin = 0, end = 0;
+    if ((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u) {
+        begin = __ldg(g.box + cell);
+        end = __ldg(g.box + cell + 1);
+    }
+    f.i = begin;
+    f.end = end;
+}
+
+// Leave the current cell (A10/code.cl:766-785).  Returns true when the walk is over.
+RT_DEV bool flatLeave(FlatWalker& f) {
+    Walker& w = f.w;
+    if (w.h.i != 0xFFFFFFFFu) return true;
+    float t = f.maxt;
+    w.t = t;
+    if (t == w.ax.t_next) {
+        w.ax.t_next += w.ax.delta_t;
+        if (t >= w.tmax_b) return true;
+        w.ax.slab += w.ax.step;
+        if (w.ax.slab == w.ax.limit) return true;
+    } else if (t == w.ay.t_next) {
+        w.ay.t_next += w.ay.delta_t;
+        if (t >= w.tmax_b) return true;
+        w.ay.slab += w.ay.step;
+        if (w.ay.slab == w.ay.limit) return true;
+    } else {
+        w.az.t_next += w.az.delta_t;
+        if (t >= w.tmax_b) return true;
+        w.az.slab += w.az.step;
+        if (w.az.slab == w.az.limit) return true;
+    }
+    return false;
+}
+
+// Test reference f.i of the current cell (A10/code.cl:882-897) and advance the cursor.
+template <int PRIM, bool ANY>
+RT_DEV void flatTest(FlatWalker& f, const GridView& g) {
+    Walker& w = f.w;
+    unsigned i = f.i;
+    float ti, be = 0.f, ga = 0.f;
+    bool v;
+    if (PRIM == PRIM_SPHERE) {
+        float4 s = __ldg(g.prim + i);
+        v = interSphere(w.o, w.d, w.a_dd, f.mint, f.maxt, s, ti);
+    } else {
+        float4 q0 = __ldg(g.prim + 3 * i), q1 = __ldg(g.prim + 3 * i + 1), q2 = __ldg(g.prim + 3 * i + 2);
+        v = interTriangle<true>(w.o, w.d, f.mint, f.maxt, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
+    }
+    f.i = i + 1;
+    if (v && ti < w.h.t) {
+        w.h.t = ti;
+        w.h.i = i;
+        w.h.beta = be;
+        w.h.gamma = ga;
+        if (ANY) f.i = f.end;   // `break` of the any-hit kernels
+    }
+}
+
+// Closest-hit (ANY = false) or any-hit (ANY = true) walk run to completion.  `maxt_in` is the
+// STORED ray.maxt.  Returns hit.i != ~0u when a primitive was accepted.
+template <int PRIM, bool ANY, bool TRI_INCL, bool STATS, bool OCC = false>
+RT_DEV Hit gridWalk(f3 o, f3 d, float maxt_in, const GridView& g, const AabbHit& binter, WalkStats* st) {
+    Walker w;
+    walkInit(w, PRIM, o, d, maxt_in, g, binter);
+    while (!walkCell<PRIM, ANY, TRI_INCL, STATS, OCC>(w, g, st)) {}
+    return w.h;
 }
 
 // ---------------------------------------------------------------------------------------

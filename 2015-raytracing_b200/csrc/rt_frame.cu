@@ -237,7 +237,9 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     r->pixels = (size_t)r->o.cols * r->o.rows;
     r->local_slots = r->pixels * r->slots_pp;
     if ((unsigned long long)r->pixels * r->o.rays_per_pixel > 0xFFFFFFFFull) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: total_rays exceeds the reference's uint range"); }
-    size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)1 << 20;
+    // default tile: 4 Mi slots -- large enough that every lane of the persistent queue walkers pops
+    // several tasks (their load balancing needs a deep queue); state ~116 B/slot streams through HBM
+    size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)1 << 22;
     size_t px_per_tile = want / r->slots_pp;
     if (px_per_tile == 0) px_per_tile = 1;
     if (px_per_tile > r->pixels) px_per_tile = r->pixels;
@@ -248,17 +250,19 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     A((void**)&r->acu, sizeof(float4) * r->local_slots);
     A((void**)&r->accum, sizeof(float4) * r->pixels);
     A((void**)&r->pixel, sizeof(uchar4) * r->pixels);
-    A((void**)&r->rays, sizeof(Ray) * r->tile_slots);
-    A((void**)&r->pois, sizeof(Poi10) * r->tile_slots);
-    A((void**)&r->shadow, sizeof(Ray) * r->tile_slots);
+    if (r->o.mode == 1) {   // the kernel-by-kernel schedule keeps the reference's AoS state per tile
+        A((void**)&r->rays, sizeof(Ray) * r->tile_slots);
+        A((void**)&r->pois, sizeof(Poi10) * r->tile_slots);
+        A((void**)&r->shadow, sizeof(Ray) * r->tile_slots);
+    }
     A((void**)&r->d_counters, sizeof(unsigned long long) * 2);
     A((void**)&r->d_profile, sizeof(unsigned long long) * 16);
     if (!rc) rc = rt_buffer_fill(ctx, r->d_profile, 0, sizeof(unsigned long long) * 16);
     if (!rc && (cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess)) rc = RT_ERR_CUDA;
     // prepareInitAcu (A10/code.js:1078-1099): zero once, never again between passes
     if (!rc) rc = rt_buffer_fill(ctx, r->acu, 0, sizeof(float4) * r->local_slots);
-    if (!rc) rc = rt_buffer_fill(ctx, r->pois, 0, sizeof(Poi10) * r->tile_slots);
-    if (!rc) rc = rt_buffer_fill(ctx, r->rays, 0, sizeof(Ray) * r->tile_slots);
+    if (!rc && r->pois) rc = rt_buffer_fill(ctx, r->pois, 0, sizeof(Poi10) * r->tile_slots);
+    if (!rc && r->rays) rc = rt_buffer_fill(ctx, r->rays, 0, sizeof(Ray) * r->tile_slots);
     if (rc) { rt_render_destroy(r); return rc; }
     *out = r;
     return RT_OK;
@@ -269,7 +273,8 @@ int rt_render_destroy(rt_render* r) {
     rt_ctx* ctx = r->ctx;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rays, r->pois, r->shadow, r->d_counters, r->d_profile};
+    void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rays, r->pois, r->shadow, r->d_counters, r->d_profile,
+                    r->w_ray, r->w_poi, r->w_atte, r->w_sh, r->w_queue, r->w_qctr};
     for (void* b : bufs) if (b) cudaFree(b);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);

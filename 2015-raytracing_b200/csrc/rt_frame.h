@@ -39,6 +39,13 @@ struct rt_render {
     rt::Ray* rays = nullptr;
     rt::Poi10* pois = nullptr;
     rt::Ray* shadow = nullptr;
+    // wavefront path (rt_wavefront.cu): per-tile SoA state, task queues, queue counters
+    float4* w_ray = nullptr;         // [2*n]: (o.xyz, mint) (d.xyz, maxt)
+    float4* w_poi = nullptr;         // [2*n]: (p.xyz, matId bits) (normal.xyz, 0)
+    float4* w_atte = nullptr;        // [n]
+    float4* w_sh = nullptr;          // [2*n]: shadow ray (o.xyz, mint) (d.xyz, maxt)
+    unsigned* w_queue = nullptr;     // [n] slot ids of the current heavy-set walk
+    unsigned* w_qctr = nullptr;      // [2*kMaxStages]: per walk stage {count, head}
     // stats
     unsigned long long* d_counters = nullptr;   // [0] closest rays, [1] any rays
     unsigned long long* d_profile = nullptr;    // 16 work counters (rt_render_read_profile)

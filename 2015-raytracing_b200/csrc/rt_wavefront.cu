@@ -253,6 +253,436 @@ int buildSceneDev(rt_render* r, SceneDev& sc) {
     return RT_OK;
 }
 
+
+// =======================================================================================
+// Wavefront path (mode 0): the pass as a short sequence of per-slot "stage" kernels and
+// queue-driven persistent "walk" kernels.
+//
+// Why: in the megakernel a warp that enters the DDA of a big grid runs until its slowest lane
+// is done while most lanes idle (rays that miss the grid's AABB, short walks) -- ncu measured
+// 4.6 of 32 lanes active per instruction (profiles/).  Here the cheap, uniform work (ray
+// generation, the small 1-cell sets, shading) stays one-thread-per-slot, while every ray that
+// must walk a BIG grid ("heavy" set) is pushed -- warp ballot + popc prefix + one atomicAdd per
+// warp -- into a compact queue of slot ids, and a persistent kernel walks the queue, refilling
+// idle lanes one cell step at a time, so its warps stay full regardless of which slots are
+// live, blocked, or missed the box.  Per-slot results are bit-identical to the other modes:
+// the same device functions run in the same per-slot order.
+// =======================================================================================
+constexpr int kMaxStages = 64;
+
+struct WaveState {
+    float4* ray;      // [2n]
+    float4* poi;      // [2n]
+    float4* atte;     // [n]
+    float4* sh;       // [2n]
+    unsigned* queue;  // [n]
+    unsigned* qctr;   // {count, head} per walk stage
+};
+
+// What one per-slot stage kernel does, in this order (all fields uniform across the grid):
+//   shade_light >= 0 : sceneRender for that light with the current shadow ray
+//   gen == 1/2       : initTrace / bouncePaths -> new ray
+//   light_render     : lightRender for every light (primary segment, after the closest pass)
+//   shadow_light >= 0: initShadowTrace for that light -> new shadow ray
+//   inline sets [set_lo, set_hi) against the current ray (kind 0 = closest, 1 = any hit)
+//   push_set >= 0    : AABB-test the ray against that heavy set and enqueue the slot
+struct StageOp {
+    int shade_light, gen, light_render, shadow_light, kind, set_lo, set_hi, push_set, qslot;
+};
+
+RT_DEV void pushTask(bool want, unsigned id, unsigned* queue, unsigned* count) {
+    unsigned m = __ballot_sync(0xffffffffu, want);
+    if (!m) return;
+    unsigned lane = threadIdx.x & 31;
+    unsigned base = 0;
+    int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = id;
+}
+
+__global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SceneDev sc, const __grid_constant__ PathArgs a,
+                                               const __grid_constant__ WaveState w, const __grid_constant__ StageOp op) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    bool inb = id < a.n_local;
+    unsigned n_closest = 0, n_any = 0;
+    bool want_push = false;
+    if (inb) {
+        const unsigned n = a.n_local;
+        PoiR poi;
+        RayR ray, sr;
+        bool poi_dirty = false, ray_dirty = false, sr_dirty = false, atte_dirty = false;
+        // ---- load what this stage needs
+        if (op.gen != 1) {
+            float4 p0 = w.poi[id], p1 = w.poi[n + id];
+            poi.p = mk3(p0.x, p0.y, p0.z); poi.matId = __float_as_int(p0.w);
+            poi.n = mk3(p1.x, p1.y, p1.z);
+            float4 at = w.atte[id];
+            poi.atte = mk3(at.x, at.y, at.z);
+        }
+        bool need_ray = (op.gen == 0) && (op.light_render || (op.kind == 0 && (op.set_hi > op.set_lo || op.push_set >= 0)));
+        if (need_ray) {
+            float4 r0 = w.ray[id], r1 = w.ray[n + id];
+            ray.o = mk3(r0.x, r0.y, r0.z); ray.mint = r0.w;
+            ray.d = mk3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
+        }
+        bool need_sr = (op.shade_light >= 0) || (op.shadow_light < 0 && op.kind == 1 && (op.set_hi > op.set_lo || op.push_set >= 0));
+        if (need_sr) {
+            float4 s0 = w.sh[id], s1 = w.sh[n + id];
+            sr.o = mk3(s0.x, s0.y, s0.z); sr.mint = s0.w;
+            sr.d = mk3(s1.x, s1.y, s1.z); sr.maxt = s1.w;
+        }
+        int seed = 0;
+        bool seed_loaded = false, seed_dirty = false;
+        float4 acu;
+        bool acu_loaded = false;
+        // ---- sceneRender of the previous shadow ray (A10/code.cl:1323-1364)
+        if (op.shade_light >= 0 && poi.matId >= 0) {
+            const LightDev& L = sc.lights[op.shade_light];
+            f3 shade = neeShade(poi.p, poi.n, sr.d, sr.maxt != sr.mint, L.scene);
+            float4 color = __ldg(sc.materials + poi.matId);
+            f3 c = mk3(color.x, color.y, color.z);
+            f3 contrib = (c * poi.atte) * shade;
+            poi.atte = poi.atte * c;
+            atte_dirty = true;
+            acu = a.acu[id]; acu_loaded = true;
+            acu = make_float4(acu.x + contrib.x, acu.y + contrib.y, acu.z + contrib.z, acu.w + 1.0f);
+        }
+        // ---- new ray
+        if (op.gen == 1) {   // initTrace (A10/code.cl:458-543)
+            Camera cam = floatToCamera(a.cam.v);
+            AABB bound = toAABB(sc.bound);
+            size_t pix = a.pixel_base + id / a.slots_pp;
+            unsigned k = a.slot_begin + id % a.slots_pp;
+            unsigned col = (unsigned)(pix % cam.cols), row = (unsigned)(pix / cam.cols);
+            ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 0.f);
+            ray.mint = RT_INF; ray.maxt = RT_INF;
+            poi.p = mk3(0.f, 0.f, 0.f); poi.n = mk3(0.f, 0.f, 0.f);
+            poi.atte = mk3(1.0f, 1.0f, 1.0f);
+            poi.matId = -1;
+            poi_dirty = atte_dirty = true;
+            bool have_ray = true;
+            f2 coord;
+            if (a.rays_per_pixel > 1) {
+                unsigned side = (unsigned)sqrtf((float)a.rays_per_pixel);
+                if (k >= side * side) have_ray = false;
+                unsigned i = k / side, j = k % side;
+                float delta = 1.0f / (float)side;
+                coord.y = delta / 2.0f;
+                for (unsigned q = 0; q < i; q++) coord.y += delta;
+                coord.x = delta / 2.0f;
+                for (unsigned q = 0; q < j; q++) coord.x += delta;
+            } else {
+                float2 c = a.rpp1_coords[pix];
+                coord.x = c.x; coord.y = c.y;
+            }
+            if (have_ray) {
+                f3 focal_point = getFocalPoint(cam, (float)col, (float)row, a.focal_length);
+                getThinLensRay(cam, focal_point, a.lens_rad, coord, ray.o, ray.d);
+                AabbHit inter = interAABB(ray.o, ray.d, bound);
+                if (inter.v) { ray.mint = inter.tmin; ray.maxt = inter.tmax; }
+            }
+            ray_dirty = true;
+            if (ray.mint != ray.maxt) n_closest++;
+        } else if (op.gen == 2) {   // bouncePaths (A10/code.cl:581-598)
+            if (poi.matId >= 0) {
+                seed = a.seeds[id]; seed_loaded = true;
+                getHemisphereRay(poi.p, poi.n, seed, ray.o, ray.d);
+                seed_dirty = true;
+                ray.mint = 0.0f; ray.maxt = RT_INF;
+                n_closest++;
+            } else {
+                ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 0.f);
+                ray.mint = RT_INF; ray.maxt = RT_INF;
+            }
+            ray_dirty = true;
+        }
+        // ---- lightRender for every light (A10/code.cl:600-629)
+        if (op.light_render) {
+            for (int l = 0; l < sc.n_lights; l++) {
+                if (ray.mint == ray.maxt) continue;
+                const LightArg& L = sc.lights[l].light;
+                f3 irradiance = normalize(mk3(L.v[6], L.v[7], L.v[8]));
+                float t;
+                if (!interLight(ray.o, ray.d, mk3(L.v[0], L.v[1], L.v[2]), mk3(L.v[3], L.v[4], L.v[5]), L.v[9], t) || t >= ray.maxt) continue;
+                ray.mint = RT_INF; ray.maxt = RT_INF;
+                ray_dirty = true;
+                poi.matId = -1;
+                poi_dirty = true;
+                if (!acu_loaded) { acu = a.acu[id]; acu_loaded = true; }
+                acu = make_float4(acu.x + irradiance.x, acu.y + irradiance.y, acu.z + irradiance.z, acu.w + 1.0f);
+            }
+        }
+        // ---- new shadow ray (A10/code.cl:631-673)
+        if (op.shadow_light >= 0) {
+            if (poi.matId >= 0) {
+                if (!seed_loaded) { seed = a.seeds[id]; seed_loaded = true; }
+                sr = makeShadowRay(poi.p, poi.n, sc.lights[op.shadow_light].shadow, seed);
+                seed_dirty = true;
+                if (sr.mint != sr.maxt) n_any++;
+            } else {
+                sr.o = mk3(0.f, 0.f, 0.f); sr.d = mk3(0.f, 0.f, 0.f);
+                sr.mint = RT_INF; sr.maxt = RT_INF;
+            }
+            sr_dirty = true;
+        }
+        // ---- small sets inline, in set order
+        if (op.kind == 0) {
+            for (int s = op.set_lo; s < op.set_hi; s++) {
+                float m0 = ray.maxt; int id0 = poi.matId;
+                closestSet<false, false>(sc.sets[s], ray, poi, nullptr);
+                if (ray.maxt != m0 || poi.matId != id0) { ray_dirty = true; poi_dirty = true; }
+            }
+            if (op.push_set >= 0 && ray.mint != ray.maxt) want_push = interAABB(ray.o, ray.d, sc.sets[op.push_set].g.bound).v;
+        } else {
+            for (int s = op.set_lo; s < op.set_hi; s++) {
+                float m0 = sr.mint, x0 = sr.maxt;
+                anySet<false, false>(sc.sets[s], sr, nullptr);
+                if (sr.mint != m0 || sr.maxt != x0) sr_dirty = true;
+            }
+            if (op.push_set >= 0 && sr.mint != sr.maxt) want_push = interAABB(sr.o, sr.d, sc.sets[op.push_set].g.bound).v;
+        }
+        // ---- write back
+        if (ray_dirty) {
+            w.ray[id] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+            w.ray[n + id] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+        }
+        if (poi_dirty) {
+            w.poi[id] = make_float4(poi.p.x, poi.p.y, poi.p.z, __int_as_float(poi.matId));
+            w.poi[n + id] = make_float4(poi.n.x, poi.n.y, poi.n.z, 0.f);
+        }
+        if (atte_dirty) w.atte[id] = make_float4(poi.atte.x, poi.atte.y, poi.atte.z, 0.f);
+        if (sr_dirty) {
+            w.sh[id] = make_float4(sr.o.x, sr.o.y, sr.o.z, sr.mint);
+            w.sh[n + id] = make_float4(sr.d.x, sr.d.y, sr.d.z, sr.maxt);
+        }
+        if (seed_dirty) a.seeds[id] = seed;
+        if (acu_loaded) a.acu[id] = acu;
+    }
+    if (op.push_set >= 0) pushTask(want_push, id, w.queue, w.qctr + 2 * op.qslot);
+    for (int d = 16; d > 0; d >>= 1) {
+        n_closest += __shfl_down_sync(0xffffffffu, n_closest, d);
+        n_any += __shfl_down_sync(0xffffffffu, n_any, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (n_closest) atomicAdd(a.counters + 0, (unsigned long long)n_closest);
+        if (n_any) atomicAdd(a.counters + 1, (unsigned long long)n_any);
+    }
+}
+
+// Persistent queue walker for one heavy set.  Each lane owns at most one ray; a lane whose walk
+// ended writes its result and becomes idle; when at least kRefill lanes of the warp are idle (or
+// none has work) the warp pops that many slot ids with ONE atomicAdd and the idle lanes set up
+// their DDA.  Every lane then advances its own ray by exactly one cell (walkCell).
+constexpr int kRefill = 8;
+
+template <int PRIM, bool ANY>
+__global__ void __launch_bounds__(256) k_walk(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w, unsigned n, int qslot) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned count = w.qctr[2 * qslot];
+    unsigned* head = w.qctr + 2 * qslot + 1;
+    const float4* src = ANY ? w.sh : w.ray;
+    FlatWalker f;
+    unsigned slot = 0;
+    bool have = false;
+    bool drained = false;   // warp-uniform: the queue has no more tasks
+    while (true) {
+        unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (!drained && (__popc(idle) >= kRefill || idle == 0xffffffffu)) {
+            unsigned base = 0;
+            int leader = __ffs(idle) - 1;
+            if ((int)lane == leader) base = atomicAdd(head, (unsigned)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have) {
+                unsigned idx = base + __popc(idle & ((1u << lane) - 1u));
+                if (idx < count) {
+                    slot = w.queue[idx];
+                    float4 r0 = src[slot], r1 = src[n + slot];
+                    f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
+                    AabbHit binter = interAABB(o, d, set.g.bound);   // true by construction (the pusher tested it)
+                    walkInit(f.w, PRIM, o, d, r1.w, set.g, binter);
+                    flatEnter(f, set.g);
+                    have = true;
+                }
+            }
+            if (base + __popc(idle) >= count) drained = true;
+            idle = __ballot_sync(0xffffffffu, !have);
+        }
+        if (idle == 0xffffffffu) break;   // nothing left in the queue and no lane has work
+        if (have) {
+            bool done = false;
+            if (f.i < f.end) flatTest<PRIM, ANY>(f, set.g);
+            if (f.i >= f.end) {
+                done = flatLeave(f);
+                if (!done) flatEnter(f, set.g);
+            }
+            if (done) {
+                have = false;
+                const Hit& h = f.w.h;
+                if (ANY) {   // sphereShadowTrace / triangleShadowTrace tail (A10/code.cl:1185-1192)
+                    if (h.i != 0xFFFFFFFFu) {
+                        float4 s0 = w.sh[slot];
+                        w.sh[slot] = make_float4(s0.x, s0.y, s0.z, h.t);
+                        float4 s1 = w.sh[n + slot];
+                        w.sh[n + slot] = make_float4(s1.x, s1.y, s1.z, h.t);
+                    }
+                } else if (h.i != 0xFFFFFFFFu) {   // closest-hit tail (A10/code.cl:921-934)
+                    f3 p = getPoint(f.w.o, f.w.d, h.t);
+                    f3 nrm;
+                    int m;
+                    if (PRIM == PRIM_SPHERE) {
+                        float4 sp = __ldg(set.g.prim + h.i);
+                        nrm = normalize(p - mk3(sp.x, sp.y, sp.z));
+                        m = (int)__ldg(set.matid + h.i);
+                    } else {
+                        float4 n0 = __ldg(set.normals + 3 * h.i), n1 = __ldg(set.normals + 3 * h.i + 1), n2 = __ldg(set.normals + 3 * h.i + 2);
+                        nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
+                        m = set.matid ? (int)__ldg(set.matid + h.i) : (int)set.scalar_matid;
+                    }
+                    float4 r1 = w.ray[n + slot];
+                    w.ray[n + slot] = make_float4(r1.x, r1.y, r1.z, h.t);
+                    w.poi[slot] = make_float4(p.x, p.y, p.z, __int_as_float(m));
+                    w.poi[n + slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+                }
+            }
+        }
+    }
+}
+
+// Builds the stage list for a scene (host) and runs one tile through it.
+struct Stage { bool is_walk; StageOp op; int set; bool any; int qslot; };
+
+bool isHeavy(const SceneSet& s) { return s.grid.n_slabs > 2 && s.grid.n_refs > 64 && s.grid.occupancy != nullptr; }
+
+// Appends the stages that trace the current ray kind against all sets, in set order.  `first` is
+// a per-slot op already holding the work that precedes the trace (shade / gen / shadow gen).
+void appendTrace(std::vector<Stage>& st, const rt_scene* sc, StageOp first, int kind, int& qslot) {
+    StageOp cur = first;
+    cur.kind = kind;
+    bool cur_used = true;   // `first` must be emitted even if empty of set work
+    int nset = (int)sc->sets.size();
+    int s = 0;
+    StageOp blank = {-1, 0, 0, -1, kind, 0, 0, -1, 0};
+    while (s < nset) {
+        if (!isHeavy(sc->sets[s])) {
+            int e = s;
+            while (e < nset && !isHeavy(sc->sets[e])) e++;
+            cur.set_lo = s; cur.set_hi = e;
+            cur_used = true;
+            s = e;
+        } else {
+            cur.push_set = s;
+            cur.qslot = qslot;
+            st.push_back({false, cur, -1, false, 0});
+            st.push_back({true, blank, s, kind == 1, qslot});
+            qslot++;
+            cur = blank;
+            cur_used = false;
+            s++;
+        }
+    }
+    if (cur_used) st.push_back({false, cur, -1, false, 0});
+}
+
+int buildStages(const rt_render* r, std::vector<Stage>& st) {
+    const rt_scene* sc = r->scene;
+    int nl = (int)sc->lights.size();
+    int qslot = 0;
+    StageOp blank = {-1, 0, 0, -1, 0, 0, 0, -1, 0};
+    int pending_shade = -1;   // light whose sceneRender still has to run
+    for (unsigned seg = 0; seg <= r->o.depth; seg++) {
+        StageOp g = blank;
+        g.shade_light = pending_shade; pending_shade = -1;
+        g.gen = seg == 0 ? 1 : 2;
+        appendTrace(st, sc, g, 0, qslot);
+        for (int l = 0; l < nl; l++) {
+            StageOp h = blank;
+            h.shade_light = pending_shade; pending_shade = -1;
+            if (seg == 0 && l == 0) h.light_render = 1;
+            h.shadow_light = l;
+            appendTrace(st, sc, h, 1, qslot);
+            pending_shade = l;
+        }
+        if (nl == 0 && seg == 0) {   // lightRender is a no-op without lights; nothing to do
+        }
+    }
+    if (pending_shade >= 0) {
+        StageOp f = blank;
+        f.shade_light = pending_shade;
+        st.push_back({false, f, -1, false, 0});
+    }
+    // merge adjacent per-slot stages where the second one carries no set work of its own that
+    // depends on a walk in between (they are adjacent only when no walk separates them)
+    std::vector<Stage> out;
+    for (const Stage& s : st) {
+        if (!out.empty() && !s.is_walk && !out.back().is_walk) {
+            StageOp& a = out.back().op;
+            const StageOp& b = s.op;
+            bool a_traces = a.set_hi > a.set_lo || a.push_set >= 0;
+            // b's shade/gen/shadow come after a's set work in program order: only merge when a has none
+            if (!a_traces && a.shadow_light < 0 && a.gen == 0 && !a.light_render && b.shade_light < 0) {
+                StageOp m = b;
+                m.shade_light = a.shade_light;
+                a = m;
+                continue;
+            }
+        }
+        out.push_back(s);
+    }
+    st.swap(out);
+    if (qslot > kMaxStages) return RT_ERR_INVALID;
+    return RT_OK;
+}
+
+int ensureWaveBuffers(rt_render* r) {
+    if (r->w_ray) return RT_OK;
+    rt_ctx* ctx = r->ctx;
+    size_t n = r->tile_slots;
+    int rc = RT_OK;
+    auto A = [&](void** p, size_t bytes) { if (!rc) rc = rt_buffer_create(ctx, bytes, p); };
+    A((void**)&r->w_ray, sizeof(float4) * 2 * n);
+    A((void**)&r->w_poi, sizeof(float4) * 2 * n);
+    A((void**)&r->w_atte, sizeof(float4) * n);
+    A((void**)&r->w_sh, sizeof(float4) * 2 * n);
+    A((void**)&r->w_queue, sizeof(unsigned) * n);
+    A((void**)&r->w_qctr, sizeof(unsigned) * 2 * kMaxStages);
+    return rc;
+}
+
+int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
+    rt_ctx* ctx = r->ctx;
+    int rc = ensureWaveBuffers(r);
+    if (rc) return rc;
+    std::vector<Stage> stages;
+    rc = buildStages(r, stages);
+    if (rc) {   // more walk stages than queue counters: run the tile through the megakernel instead
+        k_pathMega<false><<<rt_blocks(a.n_local, 128), 128, 0, ctx->stream>>>(sc, a);
+        RT_LAUNCH_CHECK(ctx, "pathMega");
+        return RT_OK;
+    }
+    WaveState w = {r->w_ray, r->w_poi, r->w_atte, r->w_sh, r->w_queue, r->w_qctr};
+    RT_CUDA(ctx, cudaMemsetAsync(r->w_qctr, 0, sizeof(unsigned) * 2 * kMaxStages, ctx->stream));
+    const unsigned n = a.n_local;
+    const int walk_blocks = ctx->prop.multiProcessorCount * 4;
+    for (const Stage& s : stages) {
+        if (!s.is_walk) {
+            k_stage<<<rt_blocks(n, 256), 256, 0, ctx->stream>>>(sc, a, w, s.op);
+            RT_LAUNCH_CHECK(ctx, "wave_stage");
+        } else {
+            const SetDev& set = sc.sets[s.set];
+            if (set.kind == PRIM_SPHERE) {
+                if (s.any) k_walk<PRIM_SPHERE, true><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
+                else k_walk<PRIM_SPHERE, false><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
+            } else {
+                if (s.any) k_walk<PRIM_TRIANGLE, true><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
+                else k_walk<PRIM_TRIANGLE, false><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
+            }
+            RT_LAUNCH_CHECK(ctx, "wave_walk");
+        }
+    }
+    return RT_OK;
+}
+
 }  // namespace
 
 int rt_fused_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, const float2* rpp1_coords) {
@@ -276,8 +706,17 @@ int rt_fused_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, con
     a.acu = r->acu + slot0;
     a.counters = r->d_counters;
     a.profile = r->d_profile;
-    if (r->profile) k_pathMega<true><<<rt_blocks(n, 128), 128, 0, ctx->stream>>>(sc, a);
-    else k_pathMega<false><<<rt_blocks(n, 128), 128, 0, ctx->stream>>>(sc, a);
-    RT_LAUNCH_CHECK(ctx, "pathMega");
-    return RT_OK;
+    if (r->profile) {   // work counters: the instrumented megakernel does the same per-slot work
+        k_pathMega<true><<<rt_blocks(n, 128), 128, 0, ctx->stream>>>(sc, a);
+        RT_LAUNCH_CHECK(ctx, "pathMega(profile)");
+        return RT_OK;
+    }
+    bool any_heavy = false;
+    for (const SceneSet& s : r->scene->sets) any_heavy = any_heavy || isHeavy(s);
+    if (o.mode == 2 || !any_heavy) {   // megakernel: explicit, or nothing would be queued anyway
+        k_pathMega<false><<<rt_blocks(n, 128), 128, 0, ctx->stream>>>(sc, a);
+        RT_LAUNCH_CHECK(ctx, "pathMega");
+        return RT_OK;
+    }
+    return waveTile(r, sc, a);
 }

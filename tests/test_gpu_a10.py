@@ -179,9 +179,10 @@ def test_every_kernel_matches_oracle(rt, gpu_ctx, oracle_lib, scenes):
     assert pix[:, :3].max() > 30, "image is not trivially black"
 
 
-@pytest.mark.parametrize("mode", [1, 0])
+@pytest.mark.parametrize("mode", [1, 0, 2])
 def test_render_frame_matches_oracle(rt, oracle_lib, scenes, mode):
-    """rt_render_execute (mode 1 = reference schedule, mode 0 = fused wavefront path) vs the
+    """rt_render_execute (mode 1 = reference schedule, mode 0 = wavefront stages + queue walkers,
+    mode 2 = megakernel) vs the
     oracle's executeRender: per-pixel float accumulation within 1e-3 (BASELINE.md gate 4; in
     practice bit-exact), seed buffer equal as integers, two progressive passes."""
     o_scene, p_scene = scenes
