@@ -261,6 +261,24 @@ RT_DEV bool interTriangle(f3 o, f3 d, float mint, float maxt, f3 p0, f3 p1, f3 p
     return true;
 }
 
+// Same test on the precomputed form (p0, e1, e2) with div = dot(ng, d) supplied by the caller,
+// ng = cross(e2, e1) -- identical operations, hence identical bits, as interTriangle<true>.
+RT_DEV bool interTrianglePre(f3 o, f3 d, float mint, float maxt, float div, f3 p0, f3 e1, f3 e2, float& beta_o, float& gamma_o, float& t_out) {
+    if (div <= 0) return false;
+    float idiv = 1.0f / div;
+    f3 s = o - p0;
+    float beta = dot(cross(s, d), e2) * idiv;
+    if (beta < 0.0f || beta > 1.0f) return false;
+    float gamma = dot(cross(s, e1), d) * idiv;
+    if (gamma < 0.0f || (gamma + beta) < 0.0f || (gamma + beta) > 1.0f) return false;
+    float t = dot(cross(s, e2), e1) * -idiv;
+    if (!(t >= mint && t <= maxt)) return false;
+    beta_o = beta;
+    gamma_o = gamma;
+    t_out = t;
+    return true;
+}
+
 // A10/code.cl:391-403 (no t > 0 test -- quirk Q5).
 RT_DEV bool interLight(f3 o, f3 d, f3 light_pos, f3 light_normal, float radius, float& t_out) {
     float den = dot(d, light_normal);

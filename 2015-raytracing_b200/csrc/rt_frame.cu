@@ -102,6 +102,21 @@ __global__ void f_accumToPixel(uchar4* pixel, const float4* accum, float m, unsi
     pixel[id] = make_uchar4((unsigned char)color.x, (unsigned char)color.y, (unsigned char)color.z, 255);
 }
 
+// Face vector and edges of every triangle reference, with exactly the operations of
+// interTriangle (A10/code.cl:252-256): e1 = p1 - p0, e2 = p2 - p0, ng = cross(e2, e1).
+__global__ void f_precomputeTriangles(const float4* prim, unsigned n_refs, float4* ng, float4* pe) {
+    unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_refs) return;
+    float4 q0 = prim[3 * r], q1 = prim[3 * r + 1], q2 = prim[3 * r + 2];
+    f3 p0 = mk3(q0.x, q0.y, q0.z), p1 = mk3(q1.x, q1.y, q1.z), p2 = mk3(q2.x, q2.y, q2.z);
+    f3 e1 = p1 - p0, e2 = p2 - p0;
+    f3 g = cross(e2, e1);
+    ng[r] = make_float4(g.x, g.y, g.z, 0.f);
+    pe[3 * r] = make_float4(p0.x, p0.y, p0.z, 0.f);
+    pe[3 * r + 1] = make_float4(e1.x, e1.y, e1.z, 0.f);
+    pe[3 * r + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
+}
+
 #define RT_TRY(expr)              \
     do {                          \
         int _rc = (expr);         \
@@ -178,6 +193,10 @@ int rt_scene_create(rt_ctx* ctx, rt_scene** out) {
 int rt_scene_destroy(rt_scene* s) {
     if (!s) return RT_ERR_INVALID;
     if (s->materials) rt_buffer_release(s->ctx, s->materials);
+    for (SceneSet& st : s->sets) {
+        if (st.pre_ng) rt_buffer_release(s->ctx, st.pre_ng);
+        if (st.pre_pe) rt_buffer_release(s->ctx, st.pre_pe);
+    }
     delete s;
     return RT_OK;
 }
@@ -205,6 +224,13 @@ int rt_scene_add_set(rt_scene* s, const rt_grid* grid, const float bound[8], int
     memcpy(st.bound, bound, sizeof st.bound);
     st.is_mesh = is_mesh;
     st.mesh_matid = mesh_matid;
+    if (grid->kind == 1 && grid->n_slabs > 2 && grid->n_refs > 64 && grid->occupancy) {   // "heavy" set, see rt_wavefront.cu
+        rt_ctx* ctx = s->ctx;
+        RT_TRY(rt_buffer_create(ctx, sizeof(float4) * grid->n_refs, (void**)&st.pre_ng));
+        RT_TRY(rt_buffer_create(ctx, sizeof(float4) * 3 * (size_t)grid->n_refs, (void**)&st.pre_pe));
+        f_precomputeTriangles<<<rt_blocks(grid->n_refs, kBlock), kBlock, 0, ctx->stream>>>((const float4*)grid->prim, grid->n_refs, st.pre_ng, st.pre_pe);
+        RT_LAUNCH_CHECK(ctx, "precomputeTriangles");
+    }
     s->sets.push_back(st);
     return RT_OK;
 }

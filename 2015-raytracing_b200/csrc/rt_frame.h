@@ -9,6 +9,11 @@ struct SceneSet {
     float bound[8];
     int is_mesh;
     unsigned mesh_matid;
+    // internal, triangle sets walked by the queue walkers: per reference the face vector
+    // ng = cross(p2-p0, p1-p0) and (p0, e1 = p1-p0, e2 = p2-p0), computed ONCE with the same fp32
+    // operations interTriangle performs per test (bit-identical values, A10/code.cl:252-256)
+    float4* pre_ng = nullptr;    // [n_refs]
+    float4* pre_pe = nullptr;    // [3*n_refs]
 };
 struct SceneLight { float shadow[16], scene[16], light[16]; };
 

@@ -179,7 +179,7 @@ def test_every_kernel_matches_oracle(rt, gpu_ctx, oracle_lib, scenes):
     assert pix[:, :3].max() > 30, "image is not trivially black"
 
 
-@pytest.mark.parametrize("mode", [1, 0, 2])
+@pytest.mark.parametrize("mode", [1, 0, 2, 3])
 def test_render_frame_matches_oracle(rt, oracle_lib, scenes, mode):
     """rt_render_execute (mode 1 = reference schedule, mode 0 = wavefront stages + queue walkers,
     mode 2 = megakernel) vs the
