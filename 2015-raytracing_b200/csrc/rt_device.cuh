@@ -463,6 +463,25 @@ RT_DEV void flatEnter(FlatWalker& f, const GridView& g) {
     f.end = end;
 }
 
+// Same, consulting a coarse occupancy bitmap held in shared memory first (1 bit per
+// (2^shift)^3 cells): most cells a ray crosses lie in empty coarse blocks and cost no global load.
+RT_DEV void flatEnterMacro(FlatWalker& f, const GridView& g, const unsigned* s_macro, unsigned shift, unsigned nm) {
+    Walker& w = f.w;
+    f.mint = w.t;
+    f.maxt = cl_min(cl_min(w.ax.t_next, w.ay.t_next), w.az.t_next);
+    unsigned begin = 0, end = 0;
+    unsigned mc = ((unsigned)w.az.slab >> shift) * (nm * nm) + ((unsigned)w.ay.slab >> shift) * nm + ((unsigned)w.ax.slab >> shift);
+    if ((s_macro[mc >> 5] >> (mc & 31)) & 1u) {
+        unsigned cell = (unsigned)w.az.slab * (g.n * g.n) + (unsigned)w.ay.slab * g.n + (unsigned)w.ax.slab;
+        if ((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u) {
+            begin = __ldg(g.box + cell);
+            end = __ldg(g.box + cell + 1);
+        }
+    }
+    f.i = begin;
+    f.end = end;
+}
+
 // Leave the current cell (A10/code.cl:766-785).  Returns true when the walk is over.
 RT_DEV bool flatLeave(FlatWalker& f) {
     Walker& w = f.w;

@@ -117,6 +117,25 @@ __global__ void f_precomputeTriangles(const float4* prim, unsigned n_refs, float
     pe[3 * r + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
 }
 
+// Coarse occupancy: bit (mz,my,mx) = OR of the fine bits of its (2^sh)^3 cells.
+__global__ void f_macroOccupancy(const unsigned* occ, unsigned n, unsigned sh, unsigned nm, unsigned* macro) {
+    size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t mcells = (size_t)nm * nm * nm;
+    bool any = false;
+    if (m < mcells) {
+        unsigned mx = (unsigned)(m % nm), my = (unsigned)((m / nm) % nm), mz = (unsigned)(m / ((size_t)nm * nm));
+        unsigned f = 1u << sh;
+        for (unsigned z = mz << sh; z < min(n, (mz << sh) + f) && !any; z++)
+            for (unsigned y = my << sh; y < min(n, (my << sh) + f) && !any; y++)
+                for (unsigned x = mx << sh; x < min(n, (mx << sh) + f); x++) {
+                    size_t c = ((size_t)z * n + y) * n + x;
+                    if ((occ[c >> 5] >> (c & 31)) & 1u) { any = true; break; }
+                }
+    }
+    unsigned bits = __ballot_sync(0xffffffffu, any);
+    if ((threadIdx.x & 31) == 0 && (m >> 5) < 8192) macro[m >> 5] = bits;
+}
+
 #define RT_TRY(expr)              \
     do {                          \
         int _rc = (expr);         \
@@ -196,6 +215,7 @@ int rt_scene_destroy(rt_scene* s) {
     for (SceneSet& st : s->sets) {
         if (st.pre_ng) rt_buffer_release(s->ctx, st.pre_ng);
         if (st.pre_pe) rt_buffer_release(s->ctx, st.pre_pe);
+        if (st.macro_occ) rt_buffer_release(s->ctx, st.macro_occ);
     }
     delete s;
     return RT_OK;
@@ -224,7 +244,20 @@ int rt_scene_add_set(rt_scene* s, const rt_grid* grid, const float bound[8], int
     memcpy(st.bound, bound, sizeof st.bound);
     st.is_mesh = is_mesh;
     st.mesh_matid = mesh_matid;
-    if (grid->kind == 1 && grid->n_slabs > 2 && grid->n_refs > 64 && grid->occupancy) {   // "heavy" set, see rt_wavefront.cu
+    if (grid->n_slabs > 2 && grid->n_refs > 64 && grid->occupancy) {   // "heavy" set: coarse occupancy for the queue walkers
+        rt_ctx* ctx = s->ctx;
+        unsigned sh = 0;
+        while (((grid->n_slabs + (1u << sh) - 1) >> sh) > 64) sh++;
+        st.macro_shift = sh;
+        st.macro_n = (grid->n_slabs + (1u << sh) - 1) >> sh;
+        size_t mcells = (size_t)st.macro_n * st.macro_n * st.macro_n;
+        RT_TRY(rt_buffer_create(ctx, sizeof(unsigned) * 8192, (void**)&st.macro_occ));
+        RT_TRY(rt_buffer_fill(ctx, st.macro_occ, 0, sizeof(unsigned) * 8192));
+        f_macroOccupancy<<<rt_blocks((mcells + 31) / 32 * 32, kBlock), kBlock, 0, ctx->stream>>>((const unsigned*)grid->occupancy, grid->n_slabs, sh,
+                                                                                                 st.macro_n, st.macro_occ);
+        RT_LAUNCH_CHECK(ctx, "macroOccupancy");
+    }
+    if (grid->kind == 1 && grid->n_slabs > 2 && grid->n_refs > 64 && grid->occupancy) {   // "heavy" triangle set, see rt_wavefront.cu
         rt_ctx* ctx = s->ctx;
         RT_TRY(rt_buffer_create(ctx, sizeof(float4) * grid->n_refs, (void**)&st.pre_ng));
         RT_TRY(rt_buffer_create(ctx, sizeof(float4) * 3 * (size_t)grid->n_refs, (void**)&st.pre_pe));

@@ -14,6 +14,10 @@ struct SceneSet {
     // operations interTriangle performs per test (bit-identical values, A10/code.cl:252-256)
     float4* pre_ng = nullptr;    // [n_refs]
     float4* pre_pe = nullptr;    // [3*n_refs]
+    // internal: coarse occupancy, 1 bit per (2^macro_shift)^3 block of cells, at most 64^3 bits = 32 KB,
+    // small enough to sit in shared memory of the queue walkers (the fine bitmap is n^3 bits)
+    unsigned* macro_occ = nullptr;
+    unsigned macro_shift = 0, macro_n = 0;
 };
 struct SceneLight { float shadow[16], scene[16], light[16]; };
 

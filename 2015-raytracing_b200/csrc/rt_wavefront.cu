@@ -26,6 +26,8 @@ struct SetDev {
     int use_occ;
     const float4* pre_ng;      // heavy triangle sets: face vector per reference
     const float4* pre_pe;      // heavy triangle sets: (p0, e1, e2) per reference
+    const unsigned* macro_occ; // heavy sets: coarse occupancy (<= 64^3 bits)
+    unsigned macro_shift, macro_n;
 };
 struct LightDev { LightArg shadow, scene, light; };
 struct SceneDev {
@@ -246,6 +248,9 @@ int buildSceneDev(rt_render* r, SceneDev& sc) {
         d.use_occ = (in.grid.occupancy != nullptr && in.grid.n_slabs > 2) ? 1 : 0;
         d.pre_ng = in.pre_ng;
         d.pre_pe = in.pre_pe;
+        d.macro_occ = in.macro_occ;
+        d.macro_shift = in.macro_shift;
+        d.macro_n = in.macro_n;
     }
     for (int i = 0; i < sc.n_lights; i++) {
         memcpy(sc.lights[i].shadow.v, s->lights[i].shadow, 64);
@@ -565,14 +570,33 @@ __global__ void __launch_bounds__(256) k_walk(const __grid_constant__ SetDev set
 // reference's first rejection), 16 B per reference; survivors are compacted with ballot/popc
 // into a per-warp candidate list so the full test runs on dense lanes.
 // ---------------------------------------------------------------------------------------
-constexpr int kStepBurst = 8;      // empty-cell steps per outer iteration
-constexpr int kWalkWarps = 8;      // warps per block
+#ifndef RT_STEP_BURST
+#define RT_STEP_BURST 8
+#endif
+#ifndef RT_WALK_MINB
+#define RT_WALK_MINB 4
+#endif
+#ifndef RT_USE_MACRO
+#define RT_USE_MACRO 1
+#endif
+constexpr int kStepBurst = RT_STEP_BURST;   // empty-cell steps per outer iteration
+constexpr int kWalkWarps = 8;               // warps per block
+constexpr int kWalkMinBlocks = RT_WALK_MINB; // resident blocks per SM the register budget is tuned for
 
 template <int PRIM, bool ANY>
-__global__ void __launch_bounds__(kWalkWarps * 32) k_walk_coop(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w,
+__global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_coop(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w,
                                                               unsigned n, int qslot) {
     __shared__ unsigned s_cand[kWalkWarps][64];
     __shared__ float s_div[kWalkWarps][64];
+#if RT_USE_MACRO
+    __shared__ unsigned s_macro[8192];   // 64^3 bits
+    for (unsigned i = threadIdx.x; i < 8192; i += blockDim.x) s_macro[i] = set.macro_occ[i];
+    __syncthreads();
+    const unsigned mshift = set.macro_shift, mn = set.macro_n;
+#define RT_ENTER(f, g) flatEnterMacro(f, g, s_macro, mshift, mn)
+#else
+#define RT_ENTER(f, g) flatEnter(f, g)
+#endif
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned count = w.qctr[2 * qslot];
@@ -600,7 +624,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32) k_walk_coop(const __grid_cons
                     f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
                     AabbHit binter = interAABB(o, d, g.bound);
                     walkInit(f.w, PRIM, o, d, r1.w, g, binter);
-                    flatEnter(f, g);
+                    RT_ENTER(f, g);
                     have = true;
                 }
             }
@@ -642,7 +666,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32) k_walk_coop(const __grid_cons
                         w.poi[n + slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
                     }
                 } else {
-                    flatEnter(f, g);
+                    RT_ENTER(f, g);
                 }
             }
         }
@@ -840,7 +864,7 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
             RT_LAUNCH_CHECK(ctx, "wave_stage");
         } else {
             const SetDev& set = sc.sets[s.set];
-            const int walk_blocks = ctx->prop.multiProcessorCount * 3;   // persistent: ~one resident wave (76-80 regs x 256 threads -> 3 blocks/SM)
+            const int walk_blocks = ctx->prop.multiProcessorCount * kWalkMinBlocks;   // persistent: one resident wave
             const bool coop = r->o.mode != 3;   // mode 3 = per-lane flattened walkers (kept for comparison)
             if (set.kind == PRIM_SPHERE) {
                 if (coop) {

@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librt2015.so")
+LIB_PATH = os.environ.get("RT2015_LIB") or os.path.join(_HERE, "librt2015.so")   # override: A/B builds of the same ABI
 if not os.path.exists(LIB_PATH):
     raise ImportError(
         "librt2015.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` or "
