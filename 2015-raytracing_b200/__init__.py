@@ -11,10 +11,11 @@ The directory name is not a valid Python identifier; import it with
 ``importlib.import_module("2015-raytracing_b200")`` (see ``__graft_entry__.py``).
 """
 from . import lib  # noqa: F401  (fails loudly when librt2015.so is missing)
+from . import assignments, multi  # noqa: F401
 from .host import (  # noqa: F401
     Bounds, Camera, Light, Mesh, Renderer, Vec3, bounds2AABB, loadScene, parseMeshJSON, parsePDB,
     splitMaterialData, splitMeshData, splitSphereData, splitTriangleData,
 )
 
-__all__ = ["lib", "Bounds", "Camera", "Light", "Mesh", "Renderer", "Vec3", "bounds2AABB", "loadScene", "parseMeshJSON",
+__all__ = ["lib", "multi", "assignments", "Bounds", "Camera", "Light", "Mesh", "Renderer", "Vec3", "bounds2AABB", "loadScene", "parseMeshJSON",
            "parsePDB", "splitMaterialData", "splitMeshData", "splitSphereData", "splitTriangleData"]

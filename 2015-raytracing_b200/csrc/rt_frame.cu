@@ -198,6 +198,21 @@ int tileReferenceSchedule(rt_render* r, const float* fcam, size_t slot0, unsigne
 
 }  // namespace
 
+int rt_time_mark(rt_render* r, int cls) {
+    if (!r->timing) return RT_OK;
+    rt_ctx* ctx = r->ctx;
+    if (r->tev_used == r->tev.size()) {
+        cudaEvent_t e;
+        RT_CUDA(ctx, cudaEventCreate(&e));
+        r->tev.push_back(e);
+        r->tcls.push_back(0);
+    }
+    r->tcls[r->tev_used] = cls;
+    RT_CUDA(ctx, cudaEventRecord(r->tev[r->tev_used], ctx->stream));
+    r->tev_used++;
+    return RT_OK;
+}
+
 extern "C" {
 
 int rt_scene_create(rt_ctx* ctx, rt_scene** out) {
@@ -315,8 +330,8 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
         A((void**)&r->shadow, sizeof(Ray) * r->tile_slots);
     }
     A((void**)&r->d_counters, sizeof(unsigned long long) * 2);
-    A((void**)&r->d_profile, sizeof(unsigned long long) * 16);
-    if (!rc) rc = rt_buffer_fill(ctx, r->d_profile, 0, sizeof(unsigned long long) * 16);
+    A((void**)&r->d_profile, sizeof(unsigned long long) * 16 * RT_MAX_SETS);
+    if (!rc) rc = rt_buffer_fill(ctx, r->d_profile, 0, sizeof(unsigned long long) * 16 * RT_MAX_SETS);
     if (!rc && (cudaEventCreate(&r->ev0) != cudaSuccess || cudaEventCreate(&r->ev1) != cudaSuccess)) rc = RT_ERR_CUDA;
     // prepareInitAcu (A10/code.js:1078-1099): zero once, never again between passes
     if (!rc) rc = rt_buffer_fill(ctx, r->acu, 0, sizeof(float4) * r->local_slots);
@@ -337,6 +352,7 @@ int rt_render_destroy(rt_render* r) {
     for (void* b : bufs) if (b) cudaFree(b);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
+    for (cudaEvent_t e : r->tev) cudaEventDestroy(e);
     delete r;
     return RT_OK;
 }
@@ -388,12 +404,39 @@ int rt_render_write_local_seeds(rt_render* r, const int* host_seeds, size_t coun
 int rt_render_set_profile(rt_render* r, int on) {
     if (!r) return RT_ERR_INVALID;
     r->profile = on != 0;
-    return rt_buffer_fill(r->ctx, r->d_profile, 0, sizeof(unsigned long long) * 16);
+    return rt_buffer_fill(r->ctx, r->d_profile, 0, sizeof(unsigned long long) * 16 * RT_MAX_SETS);
+}
+
+int rt_render_read_profile_sets(rt_render* r, unsigned long long out[RT_MAX_SETS * 16]) {
+    if (!r || !out) return RT_ERR_INVALID;
+    return rt_buffer_read(r->ctx, r->d_profile, 0, sizeof(unsigned long long) * 16 * RT_MAX_SETS, out);
 }
 
 int rt_render_read_profile(rt_render* r, unsigned long long out[16]) {
     if (!r || !out) return RT_ERR_INVALID;
-    return rt_buffer_read(r->ctx, r->d_profile, 0, sizeof(unsigned long long) * 16, out);
+    unsigned long long all[RT_MAX_SETS * 16];
+    RT_TRY(rt_render_read_profile_sets(r, all));
+    for (int q = 0; q < 16; q++) {
+        out[q] = 0;
+        for (int s = 0; s < RT_MAX_SETS; s++) out[q] += all[s * 16 + q];
+    }
+    return RT_OK;
+}
+
+int rt_render_set_timing(rt_render* r, int on) {
+    if (!r) return RT_ERR_INVALID;
+    r->timing = on != 0;
+    for (int c = 0; c < RT_TIMING_CLASSES; c++) { r->class_ms[c] = 0.f; r->class_launches[c] = 0; }
+    return RT_OK;
+}
+
+int rt_render_read_timing(rt_render* r, float ms[RT_TIMING_CLASSES], unsigned launches[RT_TIMING_CLASSES]) {
+    if (!r) return RT_ERR_INVALID;
+    for (int c = 0; c < RT_TIMING_CLASSES; c++) {
+        if (ms) ms[c] = r->class_ms[c];
+        if (launches) launches[c] = r->class_launches[c];
+    }
+    return RT_OK;
 }
 
 int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pixels) {
@@ -406,6 +449,7 @@ int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pi
     unsigned long long launches0 = ctx->launches;
     RT_CUDA(ctx, cudaMemsetAsync(r->d_counters, 0, sizeof(unsigned long long) * 2, ctx->stream));
     RT_CUDA(ctx, cudaEventRecord(r->ev0, ctx->stream));
+    r->tev_used = 0;
     float2* coords = nullptr;
     if (o.rays_per_pixel == 1) {
         RT_CUDA(ctx, cudaMallocAsync((void**)&coords, sizeof(float2) * r->pixels, ctx->stream));
@@ -416,13 +460,15 @@ int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pi
         size_t rem = r->local_slots - slot0;
         unsigned n = (unsigned)(rem < r->tile_slots ? rem : r->tile_slots);
         int rc;
-        if (o.mode == 1) rc = tileReferenceSchedule(r, fcam, slot0, n, coords);
+        if (o.mode == 1) { rc = rt_time_mark(r, 6); if (!rc) rc = tileReferenceSchedule(r, fcam, slot0, n, coords); }
         else rc = rt_fused_tile(r, fcam, slot0, n, coords);
         if (rc) return rc;
     }
     if (coords) RT_CUDA(ctx, cudaFreeAsync(coords, ctx->stream));
+    RT_TRY(rt_time_mark(r, 7));
     f_sumSlots<<<rt_blocks(r->pixels, kBlock), kBlock, 0, ctx->stream>>>(r->acu, r->accum, r->pixels, r->slots_pp);
     RT_LAUNCH_CHECK(ctx, "sumSlots");
+    RT_TRY(rt_time_mark(r, -1));
     RT_CUDA(ctx, cudaEventRecord(r->ev1, ctx->stream));
     if (host_pixels) {
         // executeCopyToPixel(passes): m = 1/(rays_per_pixel*passes) rounded to fp32 (A10/code.js:1410-1415)
@@ -434,6 +480,14 @@ int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pi
     RT_CUDA(ctx, cudaMemcpyAsync(r->h_counters, r->d_counters, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RT_CUDA(ctx, cudaEventElapsedTime(&r->last_ms, r->ev0, r->ev1));
+    for (size_t i = 0; i + 1 < r->tev_used; i++) {
+        int c = r->tcls[i];
+        if (c < 0 || c >= RT_TIMING_CLASSES) continue;
+        float ms = 0.f;
+        RT_CUDA(ctx, cudaEventElapsedTime(&ms, r->tev[i], r->tev[i + 1]));
+        r->class_ms[c] += ms;
+        r->class_launches[c]++;
+    }
     r->last_launches = (unsigned)(ctx->launches - launches0);
     r->passes++;
     return RT_OK;

@@ -57,13 +57,24 @@ struct rt_render {
     unsigned* w_qctr = nullptr;      // [2*kMaxStages]: per walk stage {count, head}
     // stats
     unsigned long long* d_counters = nullptr;   // [0] closest rays, [1] any rays
-    unsigned long long* d_profile = nullptr;    // 16 work counters (rt_render_read_profile)
+    unsigned long long* d_profile = nullptr;    // [RT_MAX_SETS][16] work counters per geometry set (rt_render_read_profile*)
     bool profile = false;
     unsigned long long h_counters[2] = {0, 0};
     unsigned last_launches = 0;
     float last_ms = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // optional per-kernel-class timing (rt_render_set_timing): one event is recorded in front of
+    // every launch; the interval up to the next event is charged to that launch's class
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;
+    std::vector<int> tcls;
+    size_t tev_used = 0;
+    float class_ms[RT_TIMING_CLASSES] = {0};
+    unsigned class_launches[RT_TIMING_CLASSES] = {0};
 };
+
+// Marks the start of a launch of timing class `cls` (no-op unless timing is on).
+int rt_time_mark(rt_render* r, int cls);
 
 
 // Fused paths (rt_wavefront.cu).  `mode` as in rt_render_opts.

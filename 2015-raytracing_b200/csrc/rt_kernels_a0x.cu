@@ -1,0 +1,584 @@
+// rt_kernels_a0x.cu -- the kernels of the earlier assignments that BASELINE.json's configs 1-4
+// name (A01 = Assign01-Sphere_Ray_Tracing, A02, A03, A07, A08, A09; paths relative to
+// /root/reference), one CUDA kernel + C-ABI launcher per OpenCL kernel, same names, argument
+// order and buffer layouts.  The grid walks reuse rt_device.cuh (the DDA text is identical in
+// A07-A10 apart from the inclusive/exclusive range test of interTriangle, quirk Q9).
+//
+// float -> uchar conversions of out-of-range values are undefined in OpenCL C (quirk Q11: A01's
+// depth shade, A02's unclamped shade, A08/A09's unclamped copyToPixel).  We pick the behaviour
+// of the oracle build (x86: truncate to int32, keep the low byte) so images compare exactly;
+// the float buffers are the authoritative comparison.
+#include "rt_device.cuh"
+#include "rt_internal.h"
+
+using namespace rt;
+
+namespace {
+
+constexpr unsigned kBlock = 256;
+
+RT_DEV unsigned char f2uc(float f) { return (unsigned char)(int)f; }
+RT_DEV uchar4 mkPixel(float r, float g, float b) { return make_uchar4(f2uc(r), f2uc(g), f2uc(b), 255); }
+
+AabbArg mkAabb(const float* b) { AabbArg a; memcpy(a.v, b, sizeof a.v); return a; }
+CamArg mkCam(const float* c) { CamArg a; memcpy(a.v, c, sizeof a.v); return a; }
+GridView mkGrid(const void* prim, const void* box, const float* bound, unsigned n) {
+    GridView g;
+    g.prim = (const float4*)prim;
+    g.box = (const unsigned*)box;
+    g.occ = nullptr;
+    g.bound.pmin = f3{bound[0], bound[1], bound[2]};
+    g.bound.pmax = f3{bound[4], bound[5], bound[6]};
+    g.n = n;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------
+// A01 -- one hard-coded sphere (A01/code.cl:50-61, 63-111, 116-147).  The camera keeps rows and
+// cols as FLOATS and packs rows before cols (sE, sF).
+// ---------------------------------------------------------------------------------------
+__global__ void k_a01_raytrace(uchar4* pixels, CamArg fcam, unsigned cols, unsigned rows) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= cols * rows) return;
+    unsigned col = id % cols, row = id / cols;
+    f3 eye = mk3(fcam.v[0], fcam.v[1], fcam.v[2]), U = mk3(fcam.v[3], fcam.v[4], fcam.v[5]);
+    f3 V = mk3(fcam.v[6], fcam.v[7], fcam.v[8]), W = mk3(fcam.v[9], fcam.v[10], fcam.v[11]);
+    float width = fcam.v[12], height = fcam.v[13], frows = fcam.v[14], fcols = fcam.v[15];
+    f3 cop = (-0.5f + ((float)col + 0.5f) / fcols) * width * U + (0.5f - ((float)row + 0.5f) / frows) * height * V + (-1.0f) * W;
+    f3 o = eye;
+    f3 d = normalize(cop - o);
+    // interSphere, A01/code.cl:63-111: c = (0,0,1), r = 0.5; `/ 2*a` is (x/2)*a; exclusive range test, t0 before t1
+    f3 sc = mk3(0.0f, 0.0f, 1.0f);
+    float sr = 0.5f;
+    float a = dot(d, d);
+    float b = 2.0f * dot(o - sc, d);
+    float c = dot(o - sc, o - sc) - sr * sr;
+    float dis = b * b - 4.0f * a * c;
+    uchar4 color = make_uchar4(0, 0, 0, 255);
+    if (!(dis < 0.0f)) {
+        float sq = sqrtf(dis);
+        float t0 = (-b - sq) / 2 * a;
+        float t1 = (-b + sq) / 2 * a;
+        float t = 0.f;
+        bool v = false;
+        if (t0 > 0.0f && t0 < RT_INF) { t = t0; v = true; }
+        else if (t1 > 0.0f && t1 < RT_INF) { t = t1; v = true; }
+        if (v) {
+            unsigned char base = f2uc((1.0f - t) * 255.0f);
+            color = make_uchar4(base, base, base, 255);
+        }
+    }
+    pixels[(unsigned)fcols * row + col] = color;
+}
+
+// ---------------------------------------------------------------------------------------
+// A02 / A03 -- brute-force closest sphere (A02/code.cl:158-232, A03/code.cl:128-187).
+// Sphere records are float4 (c.xyz, RADIUS); interSphere squares the radius per test, uses
+// `/ 2*a`, fmin/fmax and an EXCLUSIVE range test (A02/code.cl:92-140).
+//
+// B200 mapping: the N-sphere loop is FP32-issue bound and every thread of a block reads the same
+// record, so records are staged through shared memory in tiles (one coalesced 16 B load per
+// thread per tile, then broadcast reads); dot(d,d) and -b's ray part are loop invariants.
+// ---------------------------------------------------------------------------------------
+constexpr unsigned kSphereTile = 1024;   // 16 KB of shared memory
+
+struct BruteHit { float t; unsigned i; };
+
+RT_DEV bool interSphereA02(f3 o, f3 d, float a, float4 s, float& t_out) {
+    f3 omc = o - mk3(s.x, s.y, s.z);
+    float b = 2.0f * dot(omc, d);
+    float c = dot(omc, omc) - s.w;   // s.w = r*r, squared once when the tile was staged (same rounding)
+    float dis = b * b - 4.0f * a * c;
+    if (dis < 0.0f) return false;
+    float sq = sqrtf(dis);
+    float t0 = (-b - sq) / 2 * a;
+    float t1 = (-b + sq) / 2 * a;
+    float tmin = fminf(t0, t1), tmax = fmaxf(t0, t1);
+    if (tmin > 0.0f && tmin < RT_INF) { t_out = tmin; return true; }
+    if (tmax > 0.0f && tmax < RT_INF) { t_out = tmax; return true; }
+    return false;
+}
+
+// every thread of the block must call this (barriers inside); `live` lanes own a ray with mint = 0, maxt = +inf
+RT_DEV BruteHit bruteForce(bool live, f3 o, f3 d, unsigned s_size, const float4* __restrict__ s_atoms, float4* tile) {
+    BruteHit h;
+    h.t = RT_INF;
+    h.i = s_size;
+    float a = dot(d, d);
+    for (unsigned base = 0; base < s_size; base += kSphereTile) {
+        unsigned n = min(kSphereTile, s_size - base);
+        __syncthreads();
+        for (unsigned j = threadIdx.x; j < n; j += blockDim.x) {
+            float4 s = __ldg(s_atoms + base + j);
+            s.w = s.w * s.w;
+            tile[j] = s;
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 4
+            for (unsigned j = 0; j < n; j++) {
+                float t;
+                if (interSphereA02(o, d, a, tile[j], t) && t < h.t) { h.t = t; h.i = base + j; }
+            }
+        }
+    }
+    return h;
+}
+
+// pinhole ray of A02-A10 (getRay, A02/code.cl:78-90 = A10/code.cl:108-119)
+RT_DEV void pinhole(const CamArg& fcam, unsigned id, Camera& cam, unsigned& col, unsigned& row, f3& o, f3& d) {
+    cam = floatToCamera(fcam.v);
+    col = id % cam.cols;
+    row = id / cam.cols;
+    getRay(cam, (float)col, (float)row, o, d);
+}
+
+template <bool CLAMP_SHADE>
+RT_DEV uchar4 shadeSphere(const Camera& cam, f3 o, f3 d, float t, float4 atom, float4 color) {
+    f3 ipoint = getPoint(o, d, t);
+    float shade = dot(cam.W, normalize(ipoint - mk3(atom.x, atom.y, atom.z)));
+    if (CLAMP_SHADE) shade = cl_clamp(shade, 0.0f, 1.0f);
+    return mkPixel(color.x * shade * 255.0f, color.y * shade * 255.0f, color.z * shade * 255.0f);
+}
+
+__global__ void __launch_bounds__(kBlock) k_a02_raytrace(uchar4* pixels, CamArg fcam, unsigned s_size, const float4* s_atoms,
+                                                         const float4* s_colors) {
+    __shared__ float4 tile[kSphereTile];
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam;
+    unsigned col, row;
+    f3 o, d;
+    pinhole(fcam, id, cam, col, row, o, d);
+    bool live = id < cam.cols * cam.rows;
+    BruteHit h = bruteForce(live, o, d, s_size, s_atoms, tile);
+    if (!live) return;
+    uchar4 color = make_uchar4(0, 0, 0, 255);
+    if (h.i < s_size) color = shadeSphere<false>(cam, o, d, h.t, __ldg(s_atoms + h.i), __ldg(s_colors + h.i));
+    pixels[id] = color;
+}
+
+__global__ void k_a03_initTrace(uchar4* pixels, CamArg fcam, Ray* rays) {   // A03/code.cl:132-143
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam;
+    unsigned col, row;
+    RayR ray;
+    pinhole(fcam, id, cam, col, row, ray.o, ray.d);
+    if (id >= cam.cols * cam.rows) return;
+    ray.mint = 0.0f;
+    ray.maxt = RT_INF;
+    storeRay(rays + id, ray);
+    pixels[id] = make_uchar4(0, 0, 0, 255);
+}
+
+__global__ void __launch_bounds__(kBlock) k_a03_molTrace(uchar4* pixels, CamArg fcam, Ray* rays, unsigned s_size, const float4* s_atoms,
+                                                         const float4* s_colors) {   // A03/code.cl:145-187
+    __shared__ float4 tile[kSphereTile];
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam = floatToCamera(fcam.v);
+    bool live = id < cam.cols * cam.rows;
+    RayR ray;
+    ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.mint = 0.f; ray.maxt = RT_INF;
+    if (live) ray = loadRay(rays + id);
+    // the stored ray always has mint = 0, maxt = +inf here (initTrace wrote it); the kernel reads them
+    // from memory, and so do we, through the same exclusive test bounds
+    BruteHit h = bruteForce(live, ray.o, ray.d, s_size, s_atoms, tile);
+    if (!live || h.i >= s_size) return;
+    rays[id].mint = h.t;
+    pixels[id] = shadeSphere<true>(cam, ray.o, ray.d, h.t, __ldg(s_atoms + h.i), __ldg(s_colors + h.i));
+}
+
+// ---------------------------------------------------------------------------------------
+// A07 -- 3-D uniform grid, primary rays, debug colouring by cell parity
+// (A07/code.cl:311-335, 337-473, 475-626)
+// ---------------------------------------------------------------------------------------
+__global__ void k_a07_initTrace(uchar4* pixels, CamArg fcam, Ray* rays, AabbArg bound_a) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam;
+    unsigned col, row;
+    RayR ray;
+    pinhole(fcam, id, cam, col, row, ray.o, ray.d);
+    if (id >= cam.cols * cam.rows) return;
+    AabbHit inter = interAABB(ray.o, ray.d, toAABB(bound_a));
+    if (inter.v) { ray.mint = inter.tmin; ray.maxt = inter.tmax; }
+    else { ray.mint = RT_INF; ray.maxt = RT_INF; }   // ray.mint = ray.maxt (= HUGE_VALF from getRay)
+    storeRay(rays + id, ray);
+    pixels[id] = make_uchar4(0, 0, 0, 255);
+}
+
+RT_DEV uchar4 cellParityColor(const Hit& h, float shade) {
+    float s = shade * 127.0f;
+    return mkPixel((float)((h.cx % 2) + 1) * s, (float)((h.cy % 2) + 1) * s, (float)((h.cz % 2) + 1) * s);
+}
+
+template <int PRIM>
+__global__ void k_a07_trace(uchar4* pixels, CamArg fcam, Ray* rays, GridView g, const float4* normals) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam = floatToCamera(fcam.v);
+    if (id >= cam.cols * cam.rows) return;
+    RayR ray = loadRay(rays + id);
+    if (ray.mint == ray.maxt) return;
+    AabbHit binter = interAABB(ray.o, ray.d, g.bound);
+    if (!binter.v) return;
+    // spheres: inclusive test; triangles: EXCLUSIVE in A07 (A07/code.cl:195, quirk Q9)
+    Hit h = gridWalk<PRIM, false, false, false>(ray.o, ray.d, ray.maxt, g, binter, nullptr);
+    if (h.i == 0xFFFFFFFFu) return;
+    rays[id].maxt = h.t;
+    float shade;
+    if (PRIM == PRIM_SPHERE) {
+        float4 s = __ldg(g.prim + h.i);
+        f3 ipoint = getPoint(ray.o, ray.d, h.t);
+        shade = cl_clamp(dot(cam.W, normalize(ipoint - mk3(s.x, s.y, s.z))), 0.0f, 1.0f);
+    } else {
+        float4 n0 = __ldg(normals + 3 * h.i), n1 = __ldg(normals + 3 * h.i + 1), n2 = __ldg(normals + 3 * h.i + 2);
+        f3 nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
+        shade = cl_clamp(dot(cam.W, nrm), 0.0f, 1.0f);
+    }
+    pixels[id] = cellParityColor(h, shade);
+}
+
+// ---------------------------------------------------------------------------------------
+// A08 / A09 -- deterministic shading with point lights (A08/code.cl:331-951, A09/code.cl:400-1040).
+// The trace kernels are textually A10's with a 48-byte Poi (no atte); A08 launches them 2-D over
+// (cols, rows), A09 1-D over total_rays -- both index slot id = cols*row+col resp. id.
+// ---------------------------------------------------------------------------------------
+__global__ void k_a08_initTrace(float4* acu, Ray* rays, Poi8* pois, AabbArg bound_a, CamArg fcam) {   // A08/code.cl:331-363
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam;
+    unsigned col, row;
+    RayR ray;
+    pinhole(fcam, id, cam, col, row, ray.o, ray.d);
+    if (id >= cam.cols * cam.rows) return;
+    AabbHit inter = interAABB(ray.o, ray.d, toAABB(bound_a));
+    if (inter.v) { ray.mint = inter.tmin; ray.maxt = inter.tmax; }
+    else { ray.mint = RT_INF; ray.maxt = RT_INF; }
+    storeRay(rays + id, ray);
+    acu[id] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    pois[id].matId = -1;
+}
+
+// A09/code.cl:400-461: one thread per slot replays the fp32 `coord += delta` accumulation (see
+// k_initTrace_strat in rt_kernels_a10.cu); rays_per_pixel == 1 is the same path (side 1, coord 0.5).
+__global__ void k_a09_initTrace(float4* acu, Ray* rays, Poi8* pois, AabbArg bound_a, CamArg fcam, float focal_length, float lens_rad,
+                                unsigned rays_per_pixel, unsigned long long total) {
+    unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    Camera cam = floatToCamera(fcam.v);
+    unsigned pix = (unsigned)(id / rays_per_pixel), k = (unsigned)(id % rays_per_pixel);
+    unsigned col = pix % cam.cols, row = pix / cam.cols;
+    acu[id] = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    pois[id].matId = -1;
+    unsigned side = (unsigned)sqrtf((float)rays_per_pixel);
+    if (k >= side * side) return;
+    f3 focal_point = getFocalPoint(cam, (float)col, (float)row, focal_length);
+    unsigned i = k / side, j = k % side;
+    float delta = 1.0f / (float)side;
+    f2 coord;
+    coord.y = delta / 2.0f;
+    for (unsigned a = 0; a < i; a++) coord.y += delta;
+    coord.x = delta / 2.0f;
+    for (unsigned a = 0; a < j; a++) coord.x += delta;
+    RayR ray;
+    getThinLensRay(cam, focal_point, lens_rad, coord, ray.o, ray.d);
+    AabbHit inter = interAABB(ray.o, ray.d, toAABB(bound_a));
+    if (inter.v) { ray.mint = inter.tmin; ray.maxt = inter.tmax; }
+    else { ray.mint = RT_INF; ray.maxt = RT_INF; }
+    storeRay(rays + id, ray);
+}
+
+__global__ void k_a089_initShadowTrace(Ray* shadow_rays, const Poi8* pois, unsigned total, f3 light_pos) {   // A08/code.cl:365-390
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    if (pois[id].matId < 0) { storeDeadRay(shadow_rays + id); return; }
+    const float4* pq = reinterpret_cast<const float4*>(pois + id);
+    float4 p = pq[0], n = pq[1];
+    f3 org = mk3(p.x, p.y, p.z) + mk3(n.x, n.y, n.z) * 0.001f;
+    storeRay(shadow_rays + id, makeRay(org, light_pos));
+}
+
+template <int PRIM>
+__global__ void k_a089_closest(unsigned total, Poi8* pois, Ray* rays, GridView g, const float4* normals, const unsigned* matid) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    RayR ray = loadRay(rays + id);
+    if (ray.mint == ray.maxt) return;
+    AabbHit binter = interAABB(ray.o, ray.d, g.bound);
+    if (!binter.v) return;
+    Hit h = gridWalk<PRIM, false, true, false>(ray.o, ray.d, ray.maxt, g, binter, nullptr);
+    if (h.i == 0xFFFFFFFFu) return;
+    rays[id].maxt = h.t;
+    f3 p = getPoint(ray.o, ray.d, h.t);
+    f3 nrm;
+    if (PRIM == PRIM_SPHERE) {
+        float4 s = __ldg(g.prim + h.i);
+        nrm = normalize(p - mk3(s.x, s.y, s.z));
+    } else {
+        float4 n0 = __ldg(normals + 3 * h.i), n1 = __ldg(normals + 3 * h.i + 1), n2 = __ldg(normals + 3 * h.i + 2);
+        nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
+    }
+    float4* pq = reinterpret_cast<float4*>(pois + id);
+    pq[0] = make_float4(p.x, p.y, p.z, 0.f);
+    pq[1] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+    pois[id].matId = (int)__ldg(matid + h.i);
+}
+
+template <int PRIM>
+__global__ void k_a089_any(unsigned total, Ray* shadow_rays, GridView g) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    RayR ray = loadRay(shadow_rays + id);
+    if (ray.mint == ray.maxt) return;
+    AabbHit binter = interAABB(ray.o, ray.d, g.bound);
+    if (!binter.v) return;
+    Hit h = gridWalk<PRIM, true, true, false>(ray.o, ray.d, ray.maxt, g, binter, nullptr);
+    if (h.i != 0xFFFFFFFFu) {
+        shadow_rays[id].maxt = h.t;
+        shadow_rays[id].mint = h.t;
+    } else {
+        shadow_rays[id].maxt = h.t;
+    }
+}
+
+__global__ void k_a089_sceneRender(float4* acu, const Poi8* pois, const Ray* shadow_rays, const float4* material, unsigned total) {   // A08/code.cl:916-939
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    int matId = pois[id].matId;
+    if (matId < 0) return;
+    float4 n = reinterpret_cast<const float4*>(pois + id)[1];
+    float shade = 0.2f;
+    RayR sr = loadRay(shadow_rays + id);
+    if (sr.maxt != sr.mint) shade += cl_clamp(dot(sr.d, mk3(n.x, n.y, n.z)), 0.0f, 1.0f);
+    float4 color = __ldg(material + matId);
+    float s = cl_clamp(shade, 0.0f, 1.0f);
+    float4 a = acu[id];
+    acu[id] = make_float4(a.x + color.x * s, a.y + color.y * s, a.z + color.z * s, a.w + 1.0f);
+}
+
+__global__ void k_a08_copyToPixel(uchar4* pixel, const float4* acu, float m, unsigned pixels) {   // A08/code.cl:941-951
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= pixels) return;
+    float4 a = acu[id];
+    pixel[id] = mkPixel(a.x * 255.0f * m, a.y * 255.0f * m, a.z * 255.0f * m);   // unclamped (Q11)
+}
+
+__global__ void k_a09_copyToPixel(uchar4* pixel, const float4* acu, float m, unsigned pixels, unsigned rays_per_pixel) {   // A09/code.cl:1023-1040
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= pixels) return;
+    const float4* a = acu + (size_t)id * rays_per_pixel;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    for (unsigned i = 0; i < rays_per_pixel; i++) {
+        float4 v = a[i];
+        cx += v.x; cy += v.y; cz += v.z;
+    }
+    float s = 255.0f * m;
+    pixel[id] = mkPixel(cx * s, cy * s, cz * s);   // unclamped (Q11)
+}
+
+#define RT_GRID1(n) rt_blocks((n), kBlock), kBlock, 0, ctx->stream
+
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------------------- A01 - A03
+int rt_a01_raytrace(rt_ctx* ctx, void* pixels, const float* fcam) {
+    RT_CHECK_CTX(ctx);
+    if (!pixels || !fcam) return RT_ERR_INVALID;
+    unsigned rows = (unsigned)fcam[14], cols = (unsigned)fcam[15];   // A01 packs rows first
+    if (!rows || !cols) return RT_OK;
+    k_a01_raytrace<<<RT_GRID1((size_t)cols * rows)>>>((uchar4*)pixels, mkCam(fcam), cols, rows);
+    RT_LAUNCH_CHECK(ctx, "A01 raytrace");
+    return RT_OK;
+}
+
+int rt_a02_raytrace(rt_ctx* ctx, void* pixels, const float* fcam, unsigned s_size, const void* s_atoms, const void* s_colors) {
+    RT_CHECK_CTX(ctx);
+    if (!pixels || !fcam || (s_size && (!s_atoms || !s_colors))) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a02_raytrace<<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), s_size, (const float4*)s_atoms, (const float4*)s_colors);
+    RT_LAUNCH_CHECK(ctx, "A02 raytrace");
+    return RT_OK;
+}
+
+int rt_a03_initTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays) {
+    RT_CHECK_CTX(ctx);
+    if (!pixels || !fcam || !rays) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a03_initTrace<<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays);
+    RT_LAUNCH_CHECK(ctx, "A03 initTrace");
+    return RT_OK;
+}
+
+int rt_a03_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms, const void* s_colors) {
+    RT_CHECK_CTX(ctx);
+    if (!pixels || !fcam || !rays || (s_size && (!s_atoms || !s_colors))) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a03_molTrace<<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, s_size, (const float4*)s_atoms, (const float4*)s_colors);
+    RT_LAUNCH_CHECK(ctx, "A03 molTrace");
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------- A07
+int rt_a07_initTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, const float* bound) {
+    RT_CHECK_CTX(ctx);
+    if (!pixels || !fcam || !rays || !bound) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a07_initTrace<<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, mkAabb(bound));
+    RT_LAUNCH_CHECK(ctx, "A07 initTrace");
+    return RT_OK;
+}
+
+int rt_a07_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms, const void* s_mindex,
+                    const void* m_color, const float* bound, unsigned n_slabs, const void* slab_size) {
+    RT_CHECK_CTX(ctx);
+    (void)s_size; (void)s_mindex; (void)m_color;   // the kernel colours by cell parity; the material lookup is commented out in the reference
+    if (!pixels || !fcam || !rays || !s_atoms || !bound || !n_slabs || !slab_size) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a07_trace<PRIM_SPHERE><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, mkGrid(s_atoms, slab_size, bound, n_slabs), nullptr);
+    RT_LAUNCH_CHECK(ctx, "A07 molTrace");
+    return RT_OK;
+}
+
+int rt_a07_meshTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos, const void* t_normal,
+                     const void* t_mindex, const void* m_color, const float* bound, unsigned n_slabs, const void* slab_size) {
+    RT_CHECK_CTX(ctx);
+    (void)t_size; (void)t_mindex; (void)m_color;
+    if (!pixels || !fcam || !rays || !t_pos || !t_normal || !bound || !n_slabs || !slab_size) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a07_trace<PRIM_TRIANGLE><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, mkGrid(t_pos, slab_size, bound, n_slabs),
+                                                (const float4*)t_normal);
+    RT_LAUNCH_CHECK(ctx, "A07 meshTrace");
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------- A08
+int rt_a08_initTrace(rt_ctx* ctx, void* acu, void* rays, void* pois, const float* bound, const float* fcam) {
+    RT_CHECK_CTX(ctx);
+    if (!acu || !rays || !pois || !bound || !fcam) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a08_initTrace<<<RT_GRID1(n)>>>((float4*)acu, (Ray*)rays, (Poi8*)pois, mkAabb(bound), mkCam(fcam));
+    RT_LAUNCH_CHECK(ctx, "A08 initTrace");
+    return RT_OK;
+}
+
+int rt_a09_initShadowTrace(rt_ctx* ctx, void* shadow_rays, void* pois, unsigned total_rays, const float* light_pos) {
+    RT_CHECK_CTX(ctx);
+    if (!shadow_rays || !pois || !light_pos) return RT_ERR_INVALID;
+    if (!total_rays) return RT_OK;
+    k_a089_initShadowTrace<<<RT_GRID1(total_rays)>>>((Ray*)shadow_rays, (const Poi8*)pois, total_rays, f3{light_pos[0], light_pos[1], light_pos[2]});
+    RT_LAUNCH_CHECK(ctx, "initShadowTrace");
+    return RT_OK;
+}
+int rt_a08_initShadowTrace(rt_ctx* ctx, void* shadow_rays, void* pois, unsigned cols, unsigned rows, const float* light_pos) {
+    return rt_a09_initShadowTrace(ctx, shadow_rays, pois, cols * rows, light_pos);
+}
+
+int rt_a09_sphereTrace(rt_ctx* ctx, unsigned total_rays, void* pois, void* rays, const void* spheres, const void* s_matid,
+                       const void* s_box_size, const float* bound, unsigned n_slabs) {
+    RT_CHECK_CTX(ctx);
+    if (!pois || !rays || !spheres || !s_matid || !s_box_size || !bound || !n_slabs) return RT_ERR_INVALID;
+    if (!total_rays) return RT_OK;
+    k_a089_closest<PRIM_SPHERE><<<RT_GRID1(total_rays)>>>(total_rays, (Poi8*)pois, (Ray*)rays, mkGrid(spheres, s_box_size, bound, n_slabs), nullptr,
+                                                          (const unsigned*)s_matid);
+    RT_LAUNCH_CHECK(ctx, "sphereTrace");
+    return RT_OK;
+}
+int rt_a08_sphereTrace(rt_ctx* ctx, unsigned cols, unsigned rows, void* pois, void* rays, const void* spheres, const void* s_matid,
+                       const void* s_box_size, const float* bound, unsigned n_slabs) {
+    return rt_a09_sphereTrace(ctx, cols * rows, pois, rays, spheres, s_matid, s_box_size, bound, n_slabs);
+}
+
+int rt_a09_triangleTrace(rt_ctx* ctx, unsigned total_rays, void* pois, void* rays, const void* t_pos, const void* t_normal,
+                         const void* t_matid, const void* t_box_size, const float* bound, unsigned n_slabs) {
+    RT_CHECK_CTX(ctx);
+    if (!pois || !rays || !t_pos || !t_normal || !t_matid || !t_box_size || !bound || !n_slabs) return RT_ERR_INVALID;
+    if (!total_rays) return RT_OK;
+    k_a089_closest<PRIM_TRIANGLE><<<RT_GRID1(total_rays)>>>(total_rays, (Poi8*)pois, (Ray*)rays, mkGrid(t_pos, t_box_size, bound, n_slabs),
+                                                            (const float4*)t_normal, (const unsigned*)t_matid);
+    RT_LAUNCH_CHECK(ctx, "triangleTrace");
+    return RT_OK;
+}
+int rt_a08_triangleTrace(rt_ctx* ctx, unsigned cols, unsigned rows, void* pois, void* rays, const void* t_pos, const void* t_normal,
+                         const void* t_matid, const void* t_box_size, const float* bound, unsigned n_slabs) {
+    return rt_a09_triangleTrace(ctx, cols * rows, pois, rays, t_pos, t_normal, t_matid, t_box_size, bound, n_slabs);
+}
+
+int rt_a09_sphereShadowTrace(rt_ctx* ctx, unsigned total_rays, void* shadow_rays, const void* spheres, const void* s_box_size,
+                             const float* bound, unsigned n_slabs) {
+    RT_CHECK_CTX(ctx);
+    if (!shadow_rays || !spheres || !s_box_size || !bound || !n_slabs) return RT_ERR_INVALID;
+    if (!total_rays) return RT_OK;
+    k_a089_any<PRIM_SPHERE><<<RT_GRID1(total_rays)>>>(total_rays, (Ray*)shadow_rays, mkGrid(spheres, s_box_size, bound, n_slabs));
+    RT_LAUNCH_CHECK(ctx, "sphereShadowTrace");
+    return RT_OK;
+}
+int rt_a08_sphereShadowTrace(rt_ctx* ctx, unsigned cols, unsigned rows, void* shadow_rays, const void* spheres, const void* s_box_size,
+                             const float* bound, unsigned n_slabs) {
+    return rt_a09_sphereShadowTrace(ctx, cols * rows, shadow_rays, spheres, s_box_size, bound, n_slabs);
+}
+
+int rt_a09_triangleShadowTrace(rt_ctx* ctx, unsigned total_rays, void* shadow_rays, const void* t_pos, const void* t_box_size,
+                               const float* bound, unsigned n_slabs) {
+    RT_CHECK_CTX(ctx);
+    if (!shadow_rays || !t_pos || !t_box_size || !bound || !n_slabs) return RT_ERR_INVALID;
+    if (!total_rays) return RT_OK;
+    k_a089_any<PRIM_TRIANGLE><<<RT_GRID1(total_rays)>>>(total_rays, (Ray*)shadow_rays, mkGrid(t_pos, t_box_size, bound, n_slabs));
+    RT_LAUNCH_CHECK(ctx, "triangleShadowTrace");
+    return RT_OK;
+}
+int rt_a08_triangleShadowTrace(rt_ctx* ctx, unsigned cols, unsigned rows, void* shadow_rays, const void* t_pos, const void* t_box_size,
+                               const float* bound, unsigned n_slabs) {
+    return rt_a09_triangleShadowTrace(ctx, cols * rows, shadow_rays, t_pos, t_box_size, bound, n_slabs);
+}
+
+int rt_a09_sceneRender(rt_ctx* ctx, void* acu, void* pois, const void* shadow_rays, const void* material, unsigned total_rays) {
+    RT_CHECK_CTX(ctx);
+    if (!acu || !pois || !shadow_rays || !material) return RT_ERR_INVALID;
+    if (!total_rays) return RT_OK;
+    k_a089_sceneRender<<<RT_GRID1(total_rays)>>>((float4*)acu, (const Poi8*)pois, (const Ray*)shadow_rays, (const float4*)material, total_rays);
+    RT_LAUNCH_CHECK(ctx, "sceneRender");
+    return RT_OK;
+}
+int rt_a08_sceneRender(rt_ctx* ctx, void* acu, void* pois, const void* shadow_rays, const void* material, unsigned pixels) {
+    return rt_a09_sceneRender(ctx, acu, pois, shadow_rays, material, pixels);
+}
+
+int rt_a08_copyToPixel(rt_ctx* ctx, void* pixel, const void* acu, float m, unsigned pixels) {
+    RT_CHECK_CTX(ctx);
+    if (!pixel || !acu) return RT_ERR_INVALID;
+    if (!pixels) return RT_OK;
+    k_a08_copyToPixel<<<RT_GRID1(pixels)>>>((uchar4*)pixel, (const float4*)acu, m, pixels);
+    RT_LAUNCH_CHECK(ctx, "A08 copyToPixel");
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------- A09
+int rt_a09_initTrace(rt_ctx* ctx, void* acu, void* rays, void* pois, const float* bound, const float* fcam, float focal_length,
+                     float lens_rad, unsigned rays_per_pixel) {
+    RT_CHECK_CTX(ctx);
+    if (!acu || !rays || !pois || !bound || !fcam || !rays_per_pixel) return RT_ERR_INVALID;
+    unsigned long long total = (unsigned long long)(unsigned)fcam[14] * (unsigned)fcam[15] * rays_per_pixel;
+    if (!total) return RT_OK;
+    if (total > 0xFFFFFFFFull) return rt_fail(ctx, RT_ERR_INVALID, "A09 initTrace: total_rays exceeds the reference's uint range");
+    k_a09_initTrace<<<RT_GRID1(total)>>>((float4*)acu, (Ray*)rays, (Poi8*)pois, mkAabb(bound), mkCam(fcam), focal_length, lens_rad,
+                                         rays_per_pixel, total);
+    RT_LAUNCH_CHECK(ctx, "A09 initTrace");
+    return RT_OK;
+}
+
+int rt_a09_copyToPixel(rt_ctx* ctx, void* pixel, const void* acu, float m, unsigned pixels, unsigned rays_per_pixel) {
+    RT_CHECK_CTX(ctx);
+    if (!pixel || !acu) return RT_ERR_INVALID;
+    if (!pixels) return RT_OK;
+    k_a09_copyToPixel<<<RT_GRID1(pixels)>>>((uchar4*)pixel, (const float4*)acu, m, pixels, rays_per_pixel);
+    RT_LAUNCH_CHECK(ctx, "A09 copyToPixel");
+    return RT_OK;
+}
+
+}  // extern "C"

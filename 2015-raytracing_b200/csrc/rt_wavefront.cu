@@ -16,6 +16,8 @@ namespace {
 
 constexpr int kMaxSets = 8;
 constexpr int kMaxLights = 8;
+static_assert(kMaxSets == RT_MAX_SETS, "profile rows");
+#define RT_TRY_W(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
 
 struct SetDev {
     GridView g;
@@ -106,23 +108,38 @@ RT_DEV void anySet(const SetDev& s, RayR& sr, unsigned* prof) {
     else sr.maxt = h.t;
 }
 
+// Profile build only: add this thread's counters [lo,hi) to row `set` of the global table (one atomic
+// per counter per converged group of lanes) and clear them.
+RT_DEV void flushProfile(unsigned* prof, unsigned long long* table, int set, int lo, int hi) {
+    unsigned m = __activemask();
+    int leader = __ffs(m) - 1;
+    for (int q = lo; q < hi; q++) {
+        unsigned v = __reduce_add_sync(m, prof[q]);
+        if ((int)(threadIdx.x & 31) == leader && v) atomicAdd(table + set * 16 + q, (unsigned long long)v);
+        prof[q] = 0;
+    }
+}
+
 template <bool STATS>
-RT_DEV void closestAllSets(const SceneDev& sc, RayR& ray, PoiR& poi, unsigned* prof) {
+RT_DEV void closestAllSets(const SceneDev& sc, RayR& ray, PoiR& poi, unsigned* prof, unsigned long long* table) {
     for (int s = 0; s < sc.n_sets; s++) {
         if (sc.sets[s].use_occ) closestSet<true, STATS>(sc.sets[s], ray, poi, prof);
         else closestSet<false, STATS>(sc.sets[s], ray, poi, prof);
+        if (STATS) flushProfile(prof, table, s, 0, 8);
     }
 }
 
 // one light: initShadowTrace + shadow traces + sceneRender (A10/code.cl:631-673, 1073-1364)
 template <bool STATS>
-RT_DEV void shadeLight(const SceneDev& sc, const LightDev& L, PoiR& poi, int& seed, float4& acu, unsigned& n_any, unsigned* prof) {
+RT_DEV void shadeLight(const SceneDev& sc, const LightDev& L, PoiR& poi, int& seed, float4& acu, unsigned& n_any, unsigned* prof,
+                       unsigned long long* table) {
     if (poi.matId < 0) return;
     RayR sr = makeShadowRay(poi.p, poi.n, L.shadow, seed);
     if (sr.mint != sr.maxt) n_any++;
     for (int s = 0; s < sc.n_sets; s++) {
         if (sc.sets[s].use_occ) anySet<true, STATS>(sc.sets[s], sr, prof);
         else anySet<false, STATS>(sc.sets[s], sr, prof);
+        if (STATS) flushProfile(prof, table, s, 8, 14);
     }
     f3 shade = neeShade(poi.p, poi.n, sr.d, sr.maxt != sr.mint, L.scene);
     float4 color = __ldg(sc.materials + poi.matId);
@@ -180,7 +197,7 @@ __global__ void __launch_bounds__(128) k_pathMega(const __grid_constant__ SceneD
         float4 acu = a.acu[id];
         // ---- primary segment
         if (ray.mint != ray.maxt) n_closest++;
-        closestAllSets<STATS>(sc, ray, poi, prof);
+        closestAllSets<STATS>(sc, ray, poi, prof, a.profile);
         for (int l = 0; l < sc.n_lights; l++) {   // lightRender, A10/code.cl:600-629
             if (ray.mint == ray.maxt) continue;
             const LightArg& L = sc.lights[l].light;
@@ -191,7 +208,7 @@ __global__ void __launch_bounds__(128) k_pathMega(const __grid_constant__ SceneD
             poi.matId = -1;
             acu = make_float4(acu.x + irradiance.x, acu.y + irradiance.y, acu.z + irradiance.z, acu.w + 1.0f);
         }
-        for (int l = 0; l < sc.n_lights; l++) shadeLight<STATS>(sc, sc.lights[l], poi, seed, acu, n_any, prof);
+        for (int l = 0; l < sc.n_lights; l++) shadeLight<STATS>(sc, sc.lights[l], poi, seed, acu, n_any, prof, a.profile);
         // ---- bounces (A10/code.js:1829-1846)
         for (unsigned j = 0; j < a.depth; j++) {
             if (poi.matId >= 0) {   // bouncePaths, A10/code.cl:581-598
@@ -201,8 +218,8 @@ __global__ void __launch_bounds__(128) k_pathMega(const __grid_constant__ SceneD
             } else {
                 ray.mint = RT_INF; ray.maxt = RT_INF;
             }
-            closestAllSets<STATS>(sc, ray, poi, prof);
-            for (int l = 0; l < sc.n_lights; l++) shadeLight<STATS>(sc, sc.lights[l], poi, seed, acu, n_any, prof);
+            closestAllSets<STATS>(sc, ray, poi, prof, a.profile);
+            for (int l = 0; l < sc.n_lights; l++) shadeLight<STATS>(sc, sc.lights[l], poi, seed, acu, n_any, prof, a.profile);
         }
         a.seeds[id] = seed;
         a.acu[id] = acu;
@@ -216,12 +233,10 @@ __global__ void __launch_bounds__(128) k_pathMega(const __grid_constant__ SceneD
         if (n_closest) atomicAdd(a.counters + 0, (unsigned long long)n_closest);
         if (n_any) atomicAdd(a.counters + 1, (unsigned long long)n_any);
     }
-    if (STATS) {
-        for (int q = 0; q < 16; q++) {
-            unsigned v = prof[q];
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-            if ((threadIdx.x & 31) == 0 && v) atomicAdd(a.profile + q, (unsigned long long)v);
-        }
+    if (STATS) {   // slots processed (the per-set counters were flushed as they were produced)
+        unsigned v = prof[14];
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(a.profile + 14, (unsigned long long)v);
     }
 }
 
@@ -851,6 +866,7 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
     std::vector<Stage> stages;
     rc = buildStages(r, stages);
     if (rc) {   // more walk stages than queue counters: run the tile through the megakernel instead
+        RT_TRY_W(rt_time_mark(r, 5));
         k_pathMega<false><<<rt_blocks(a.n_local, 128), 128, 0, ctx->stream>>>(sc, a);
         RT_LAUNCH_CHECK(ctx, "pathMega");
         return RT_OK;
@@ -860,12 +876,14 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
     const unsigned n = a.n_local;
     for (const Stage& s : stages) {
         if (!s.is_walk) {
+            RT_TRY_W(rt_time_mark(r, 0));
             k_stage<<<rt_blocks(n, 256), 256, 0, ctx->stream>>>(sc, a, w, s.op);
             RT_LAUNCH_CHECK(ctx, "wave_stage");
         } else {
             const SetDev& set = sc.sets[s.set];
             const int walk_blocks = ctx->prop.multiProcessorCount * kWalkMinBlocks;   // persistent: one resident wave
             const bool coop = r->o.mode != 3;   // mode 3 = per-lane flattened walkers (kept for comparison)
+            RT_TRY_W(rt_time_mark(r, (set.kind == PRIM_SPHERE ? 1 : 3) + (s.any ? 1 : 0)));
             if (set.kind == PRIM_SPHERE) {
                 if (coop) {
                     if (s.any) k_walk_coop<PRIM_SPHERE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
@@ -913,6 +931,7 @@ int rt_fused_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, con
     a.counters = r->d_counters;
     a.profile = r->d_profile;
     if (r->profile) {   // work counters: the instrumented megakernel does the same per-slot work
+        RT_TRY_W(rt_time_mark(r, 5));
         k_pathMega<true><<<rt_blocks(n, 128), 128, 0, ctx->stream>>>(sc, a);
         RT_LAUNCH_CHECK(ctx, "pathMega(profile)");
         return RT_OK;
@@ -920,6 +939,7 @@ int rt_fused_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, con
     bool any_heavy = false;
     for (const SceneSet& s : r->scene->sets) any_heavy = any_heavy || isHeavy(s);
     if (o.mode == 2 || !any_heavy) {   // megakernel: explicit, or nothing would be queued anyway
+        RT_TRY_W(rt_time_mark(r, 5));
         k_pathMega<false><<<rt_blocks(n, 128), 128, 0, ctx->stream>>>(sc, a);
         RT_LAUNCH_CHECK(ctx, "pathMega");
         return RT_OK;

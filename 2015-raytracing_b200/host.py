@@ -471,8 +471,10 @@ def _vec3(e, name):
     return Vec3(_num(v, "x"), _num(v, "y"), _num(v, "z"))
 
 
-def loadScene(sceneName, width, height, mesh_loader=None):
-    """loadScene (A10/code.js:723-897).  ``width``/``height`` are the canvas globals.  Files
+def loadScene(sceneName, width, height, mesh_loader=None, assignment=10):
+    """loadScene (A10/code.js:723-897; ``assignment`` 8 / 9 select the variants of
+    A08/code.js:484-612 and A09/code.js:560-670: point lights that are a bare position, flat
+    triangle bounds padded by 1 instead of 0.1, no <mesh>, and no lens parameters in A08).  ``width``/``height`` are the canvas globals.  Files
     start with a UTF-8 BOM and contain commented-out geometry; ``getElementsByTagName`` is a
     descendant search in document order.  ``mesh_loader(file)`` may supply the parseMeshJSON
     result for a ``<mesh>`` (synthetic meshes); by default the path is resolved against the
@@ -483,10 +485,15 @@ def loadScene(sceneName, width, height, mesh_loader=None):
     xc = _first(doc, "camera")
     cam = Camera()
     cam.lookAt(_vec3(xc, "eye"), _vec3(xc, "lookAt"), _vec3(xc, "vup"), _num(xc, "fov"), width, height)
-    focal, lens = _num(xc, "focal_length"), _num(xc, "lens_diameter")
+    focal = lens = None
+    if assignment >= 9:
+        focal, lens = _num(xc, "focal_length"), _num(xc, "lens_diameter")
 
     lights = []
     for xl in doc.iter("light"):
+        if assignment < 10:
+            lights.append(_vec3(xl, "position"))
+            continue
         lt = Light()   # fields assigned directly: the light normal is NOT normalised (A10/code.js:751-757)
         lt.position, lt.normal, lt.irradiance = _vec3(xl, "position"), _vec3(xl, "normal"), _vec3(xl, "irradiance")
         lt.radius = _num(xl, "radius")
@@ -516,12 +523,13 @@ def loadScene(sceneName, width, height, mesh_loader=None):
                                     [max(max(ps[0][a], ps[1][a]), ps[2][a]) for a in range(3)]))
     for a in range(3):   # zero-thickness guard, A10/code.js:837-842
         if triangleBounds.min[a] == triangleBounds.max[a]:
-            triangleBounds.min[a] -= 0.1
-            triangleBounds.max[a] += 0.1
+            pad = 0.1 if assignment >= 10 else 1
+            triangleBounds.min[a] -= pad
+            triangleBounds.max[a] += pad
 
     sceneBounds = Bounds()
     meshes = []
-    for xm in doc.iter("mesh"):
+    for xm in (doc.iter("mesh") if assignment >= 10 else ()):
         fname = _str(xm, "file")
         jmesh = mesh_loader(fname) if mesh_loader else parseMeshJSON(os.path.join(base, fname))
         mesh = Mesh()
@@ -630,31 +638,60 @@ class Renderer:
 
     def profile_pass(self, camera=None):
         """Runs ONE extra pass with the instrumented kernel and returns the work counters of
-        rt_render_read_profile (not a timing run)."""
+        rt_render_read_profile_sets: one row of 16 counters per geometry set (not a timing run)."""
         self.ctx.check(L.dll.rt_render_set_profile(self.h_render, 1))
         try:
             self.executeRender(camera, readback=False)
-            out = (L.ULL * 16)()
-            self.ctx.check(L.dll.rt_render_read_profile(self.h_render, C.byref(out)))
+            out = (L.ULL * 128)()
+            self.ctx.check(L.dll.rt_render_read_profile_sets(self.h_render, C.byref(out)))
         finally:
             self.ctx.check(L.dll.rt_render_set_profile(self.h_render, 0))
-        return [int(v) for v in out]
+        return np.array(list(out), dtype=np.uint64).reshape(8, 16)
+
+    TIMING_CLASSES = ("stage", "walk_sphere_closest", "walk_sphere_any", "walk_triangle_closest", "walk_triangle_any", "megakernel",
+                      "reference_schedule", "sum_copy")
+
+    def set_timing(self, on=True):
+        """Per-kernel-class CUDA-event timing of the following executeRender calls."""
+        self.ctx.check(L.dll.rt_render_set_timing(self.h_render, 1 if on else 0))
+
+    def timing(self):
+        ms, n = (L.F * 8)(), (L.U * 8)()
+        self.ctx.check(L.dll.rt_render_read_timing(self.h_render, C.byref(ms), C.byref(n)))
+        return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(self.TIMING_CLASSES)}
+
+    @staticmethod
+    def traversal_bytes(p, prim_bytes_sphere=16, prim_bytes_tri=48):
+        """ALGORITHMIC traversal bytes of one row of work counters, split into the
+        closest-hit and the any-hit queries: 48 B ray load per walk + 8 B per visited cell + 16/48 B
+        per sphere/triangle test + per hit the normals (48, triangles), matid (4, not meshes), Poi
+        store (64) and maxt store (4); any-hit adds the 8 B mint/maxt store per walk."""
+        p = [int(v) for v in p]
+        closest = (48 * p[0] + 8 * p[2] + prim_bytes_sphere * p[3] + prim_bytes_tri * p[4] + p[5] * (4 + 64 + 4) + p[6] * (48 + 4 + 64 + 4)
+                   + p[7] * (48 + 64 + 4))
+        anyhit = 48 * p[8] + 8 * p[10] + prim_bytes_sphere * p[11] + prim_bytes_tri * p[12] + 8 * p[9]
+        return closest, anyhit
 
     def algorithmic_bytes(self, prof=None):
         """ALGORITHMIC bytes of one pass in the REFERENCE's data layout (restated
         in DESIGN.md): what the kernel-by-kernel schedule must move for the work this pass did.
-        Traversal, per (live ray, set) query: 48 B ray load + 8 B per visited cell + 16/48 B per
-        sphere/triangle test + hit record traffic; any-hit adds the 8 B mint/maxt store.
         Streaming kernels, per slot: initTrace 68, lightRender 48/light, bouncePaths 120,
-        initShadowTrace 120 and sceneRender 176 per light per segment; copyToPixel 16/slot + 4/px."""
-        p = prof or self.profile_pass()
+        initShadowTrace 120 and sceneRender 176 per light per segment; copyToPixel 16/slot + 4/px.
+        Also returned per geometry set (the queue walkers' share)."""
+        p = self.profile_pass() if prof is None else prof
         nl, depth = len(self.scene["lights"]), self.depth
-        slots = p[14]
-        trav = (48 * p[0] + 8 * p[2] + 16 * p[3] + 48 * p[4] + p[5] * (4 + 64 + 4) + p[6] * (48 + 4 + 64 + 4) + p[7] * (48 + 64 + 4)
-                + 48 * p[8] + 8 * p[10] + 16 * p[11] + 48 * p[12] + 8 * p[9])
+        tot = p.sum(axis=0)
+        slots = int(tot[14])
+        c, a = self.traversal_bytes(tot)
         stream = slots * (68 + 48 * nl + (1 + depth) * nl * (120 + 176) + depth * 120 + 16) + 4 * self.width * self.height
-        return {"bytes_per_pass": int(trav + stream), "traversal_bytes": int(trav), "streaming_bytes": int(stream), "profile": p,
-                "kernel": "k_pathMega (fused pass)" if self.mode != 1 else "reference schedule (all kernels)"}
+        per_set = []
+        for row in p:
+            cs, as_ = self.traversal_bytes(row)
+            per_set.append({"closest_bytes": cs, "any_bytes": as_, "closest_walks": int(row[1]), "any_walks": int(row[9]),
+                            "closest_queries": int(row[0]), "any_queries": int(row[8]),
+                            "cells": int(row[2] + row[10]), "tests": int(row[3] + row[4] + row[11] + row[12])})
+        return {"bytes_per_pass": int(c + a + stream), "traversal_bytes": int(c + a), "streaming_bytes": int(stream),
+                "profile": [int(v) for v in tot], "per_set": per_set}
 
     # -- postRender: A10/code.js:1856-1859 --
     def postRender(self):

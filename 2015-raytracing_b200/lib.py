@@ -69,6 +69,29 @@ _SIGS = {
     "rt_a10_triangleShadowTrace": ([P, U, P, P, P, P, U], I),
     "rt_a10_sceneRender": ([P, P, P, P, P, P, U], I),
     "rt_a10_copyToPixel": ([P, P, P, F, U, U], I),
+    "rt_a01_raytrace": ([P, P, P], I),
+    "rt_a02_raytrace": ([P, P, P, U, P, P], I),
+    "rt_a03_initTrace": ([P, P, P, P], I),
+    "rt_a03_molTrace": ([P, P, P, P, U, P, P], I),
+    "rt_a07_initTrace": ([P, P, P, P, P], I),
+    "rt_a07_molTrace": ([P, P, P, P, U, P, P, P, P, U, P], I),
+    "rt_a07_meshTrace": ([P, P, P, P, U, P, P, P, P, P, U, P], I),
+    "rt_a08_initTrace": ([P, P, P, P, P, P], I),
+    "rt_a08_initShadowTrace": ([P, P, P, U, U, P], I),
+    "rt_a08_sphereTrace": ([P, U, U, P, P, P, P, P, P, U], I),
+    "rt_a08_triangleTrace": ([P, U, U, P, P, P, P, P, P, P, U], I),
+    "rt_a08_sphereShadowTrace": ([P, U, U, P, P, P, P, U], I),
+    "rt_a08_triangleShadowTrace": ([P, U, U, P, P, P, P, U], I),
+    "rt_a08_sceneRender": ([P, P, P, P, P, U], I),
+    "rt_a08_copyToPixel": ([P, P, P, F, U], I),
+    "rt_a09_initTrace": ([P, P, P, P, P, P, F, F, U], I),
+    "rt_a09_initShadowTrace": ([P, P, P, U, P], I),
+    "rt_a09_sphereTrace": ([P, U, P, P, P, P, P, P, U], I),
+    "rt_a09_triangleTrace": ([P, U, P, P, P, P, P, P, P, U], I),
+    "rt_a09_sphereShadowTrace": ([P, U, P, P, P, P, U], I),
+    "rt_a09_triangleShadowTrace": ([P, U, P, P, P, P, U], I),
+    "rt_a09_sceneRender": ([P, P, P, P, P, U], I),
+    "rt_a09_copyToPixel": ([P, P, P, F, U, U], I),
     "rt_grid_build_spheres": ([P, P, P, U, P, P, U, C.POINTER(Grid)], I),
     "rt_grid_build_triangles": ([P, P, P, P, U, P, P, U, C.POINTER(MeshXform), C.POINTER(Grid)], I),
     "rt_grid_release": ([P, C.POINTER(Grid)], I),
@@ -88,6 +111,9 @@ _SIGS = {
     "rt_render_write_local_seeds": ([P, P, Z], I),
     "rt_render_set_profile": ([P, I], I),
     "rt_render_read_profile": ([P, C.POINTER(ULL * 16)], I),
+    "rt_render_read_profile_sets": ([P, C.POINTER(ULL * 128)], I),
+    "rt_render_set_timing": ([P, I], I),
+    "rt_render_read_timing": ([P, C.POINTER(F * 8), C.POINTER(U * 8)], I),
     "rt_accum_to_pixel": ([P, P, P, F, U], I),
     "rt_render_stats": ([P, C.POINTER(ULL), C.POINTER(ULL), C.POINTER(U), C.POINTER(F)], I),
 }

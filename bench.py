@@ -31,6 +31,7 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, _p)
 
 PKG = "2015-raytracing_b200"
+METRIC = "path-traced Mrays/s at 1080p"
 
 
 def parse_args():
@@ -123,29 +124,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU legs (oracle)
-def oracle_prep_from_device(rt, renderer, scene):
-    """Host copies of the buffers the GPU grid build produced (they are parity-tested against the
-    oracle's own split*Data at test sizes); fed to the oracle kernels for CPU timing."""
+def oracle_scene(args, tmp):
+    """The same synthetic scene through the ORACLE's host restatement of code.js (loadScene,
+    parseMeshJSON, split*Data, Mesh transforms) -- no product code and no GPU on this path."""
+    import synth
+    from oracle import host as OH
     from oracle import refcl as OR
-    ctx = renderer.ctx
-    prep = {"aabb": rt.bounds2AABB(scene["bounds"]), "materials": rt.splitMaterialData(scene), "sets": [], "lights": []}
-    grids = list(renderer._grids)
-    gi = 0
-    if len(scene["spheres"]) > 0:
-        d = rt.host.DeviceGrid(ctx, grids[gi], None); gi += 1
-        prep["sets"].append({"kind": "sphere", "data": d.prim(), "matid": d.matid(), "box": d.box_size(),
-                             "aabb": rt.bounds2AABB(scene["sphereBounds"]), "n": d.n_slabs})
-    if len(scene["triangles"]) > 0:
-        d = rt.host.DeviceGrid(ctx, grids[gi], None); gi += 1
-        prep["sets"].append({"kind": "triangle", "pos": d.prim(), "normal": d.normal(), "matid": d.matid(), "box": d.box_size(),
-                             "aabb": rt.bounds2AABB(scene["triangleBounds"]), "n": d.n_slabs})
-    for m in scene["meshes"]:
-        d = rt.host.DeviceGrid(ctx, m.grid, None)
-        prep["sets"].append({"kind": "mesh", "pos": d.prim(), "normal": d.normal(), "matid": int(m.matId), "box": d.box_size(),
-                             "aabb": rt.bounds2AABB(m.bounds), "n": d.n_slabs})
-    for lt in scene["lights"]:
-        prep["lights"].append({"shadow": lt.toShadowInfo(), "scene": lt.toSceneRenderInfo(), "light": lt.toLightRenderInfo()})
-    return prep
+    mesh_json = synth.synth_mesh(args.mesh_u, args.mesh_v, seed=args.seed)
+    path = synth.write_scene(tmp, n_lights=args.lights, with_sphere=True, with_mesh=True, mesh_nslabs=args.nslabs)
+    scene = OH.loadScene(path, args.cols, args.rows, mesh_loader=lambda _f: OH.parseMeshJSON(mesh_json))
+    return scene, OR.prepare_a10(scene, 1)
 
 
 def cpu_pass_rows(olib, prep, cam16, args, focal, lens_diam, row0, nrows, seeds_rows):
@@ -160,6 +148,61 @@ def cpu_pass_rows(olib, prep, cam16, args, focal, lens_diam, row0, nrows, seeds_
     OR.a10_execute_render(olib, st, prep, cam16, cols, args.rows, rpp, focal, lens_diam, depth=args.depth, row0=row0, nrows=nrows)
     dt = time.perf_counter() - t0
     return st.n_closest + st.n_any, dt
+
+
+# ------------------------------------------------------------------------------ roofline
+def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
+    """Roofline of the DOMINANT kernel: its ALGORITHMIC bytes (counted by the
+    instrumented pass on the same inputs, per geometry set) over its launch time measured with
+    CUDA events inside the timed region.  The whole step is reported next to it."""
+    alg = r.algorithmic_bytes()
+    walk = {k: v for k, v in tclass.items() if k.startswith("walk_") and v["launches"]}
+    step_ms = kern_ms / max(args.steps, 1)
+    step = {"algorithmic_bytes": alg["bytes_per_pass"], "ms": round(step_ms, 3),
+            "achieved_gbs": round(alg["bytes_per_pass"] / (step_ms * 1e-3) / 1e9, 2),
+            "class_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in tclass.items() if v["launches"]},
+            "class_launches_per_step": {k: v["launches"] // args.steps for k, v in tclass.items() if v["launches"]}}
+    if not walk:   # megakernel / reference schedule: the step is the kernel
+        achieved = step["achieved_gbs"]
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                "kernel": "k_pathMega" if args.mode == 2 else "whole pass", "peak_source": "measured" if measured_peak else "fallback",
+                "algorithmic_bytes_per_launch": alg["bytes_per_pass"], "launch_ms": round(step_ms, 3), "step": step}
+    # heavy sets (the ones the queue walkers serve), by primitive kind; rows of the work profile are in set order
+    kinds = []
+    if len(scene["spheres"]) > 0:
+        kinds.append(("sphere", r._grids[len(kinds)]))
+    if len(scene["triangles"]) > 0:
+        kinds.append(("triangle", r._grids[len(kinds)]))
+    for m in scene["meshes"]:
+        kinds.append(("triangle", m.grid))
+    byts = {"walk_sphere_closest": 0, "walk_sphere_any": 0, "walk_triangle_closest": 0, "walk_triangle_any": 0}
+    for row, (kind, g) in zip(alg["per_set"], kinds):
+        if not (g.n_slabs > 2 and g.n_refs > 64):
+            continue
+        # the walker sees only rays that hit the set's AABB: take the ray loads of the others out
+        byts["walk_%s_closest" % kind] += row["closest_bytes"] - 48 * (row["closest_queries"] - row["closest_walks"])
+        byts["walk_%s_any" % kind] += row["any_bytes"] - 48 * (row["any_queries"] - row["any_walks"])
+    dom = max(walk, key=lambda k: walk[k]["ms"])
+    per = {}
+    for k, v in walk.items():
+        n_l = v["launches"]
+        b_launch = byts[k] * args.steps / n_l
+        ms_launch = v["ms"] / n_l
+        per[k] = {"launches_per_step": n_l // args.steps, "launch_ms": round(ms_launch, 4), "algorithmic_bytes_per_launch": int(b_launch),
+                  "achieved_gbs": round(b_launch / (ms_launch * 1e-3) / 1e9, 2), "share_of_step": round(v["ms"] / kern_ms, 4)}
+    d = per[dom]
+    name = {"walk_triangle_closest": "k_walk_coop<triangle, closest hit>", "walk_triangle_any": "k_walk_coop<triangle, any hit>",
+            "walk_sphere_closest": "k_walk_coop<sphere, closest hit>", "walk_sphere_any": "k_walk_coop<sphere, any hit>"}[dom]
+    return {"bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": round(d["achieved_gbs"] / peak, 4),
+            "traffic": NCU_TRAFFIC.get(dom), "kernel": name, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if measured_peak else "fallback",
+            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "launch_ms": d["launch_ms"],
+            "share_of_step": d["share_of_step"], "kernels": per, "step": step,
+            "work_per_set": alg["per_set"][:len(kinds)]}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch (4 Mi-slot tile) of the walker kernels, from the
+# committed `ncu --set full` capture (profiles/r1_walk_full_summary.md; mean over the captured launches)
+NCU_TRAFFIC = {"walk_triangle_any": 497020757, "walk_triangle_closest": 487735552}
 
 
 # ------------------------------------------------------------------------------ main
@@ -187,8 +230,8 @@ def main():
 
     tmp = tempfile.mkdtemp(prefix="rt_bench_")
     scene = build_scene(rt, args, tmp)
-    slots_pp = args.spp // world
-    r = rt.Renderer(scene, args.cols, args.rows, args.spp, depth=args.depth, device=local_rank, slots=(rank * slots_pp, slots_pp),
+    slot_begin, slots_pp = rt.multi.slot_range(rank, world, args.spp)   # split by samples per pixel
+    r = rt.Renderer(scene, args.cols, args.rows, args.spp, depth=args.depth, device=local_rank, slots=(slot_begin, slots_pp),
                     mode=args.mode, tile_slots=args.tile_slots)
     total = args.cols * args.rows * args.spp
     # host seed array: this rank's slots only are generated/kept ([pixel][k_local]) -- same values a full
@@ -227,8 +270,7 @@ def main():
         r.executeRender(readback=False)
         s = r.stats()
         with torch.cuda.stream(ext):
-            if world > 1:
-                dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
+            rt.multi.reduce_accum(acc_t, dst=0)   # the one collective: sum of the per-pixel accumulation images
             if rank == 0:
                 m = float(np.float32(1.0 / (args.spp * (r.passes - 1))))
                 r.ctx.check(L.dll.rt_accum_to_pixel(r.ctx.h, pix_dev.data_ptr(), acc_t.data_ptr(), m, args.cols * args.rows))
@@ -272,7 +314,10 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    r.set_timing(True)   # one CUDA event in front of every launch, on the launching stream
     ms, rays, launches, kern_ms = timed(step_device, args.steps)
+    tclass = r.timing()
+    r.set_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     value = rays / (ms * 1e-3) / 1e6
     # end-to-end (host buffers, copies inside the timed region)
@@ -283,31 +328,25 @@ def main():
     out = None
     if rank == 0:
         info = r.ctx.device_info()
-        # roofline of the dominant kernel (the fused pass kernel = the whole step)
-        alg = r.algorithmic_bytes() if hasattr(r, "algorithmic_bytes") else None
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        per_launch_ms = kern_ms / max(args.steps, 1)
-        roofline = None
-        if alg is not None:
-            achieved = alg["bytes_per_pass"] / (per_launch_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                        "traffic": None, "kernel": alg["kernel"], "peak_source": "measured" if peaks else "fallback",
-                        "algorithmic_bytes_per_launch": alg["bytes_per_pass"], "launch_ms": round(per_launch_ms, 3)}
+        roofline = roofline_of(r, scene, tclass, kern_ms, args, peak, bool(peaks))
         cpu = None
         if not args.no_cpu_baseline:
-            cpu = cpu_baseline(rt, r, scene, args, cam)
+            cpu = cpu_baseline(args)
         out = {
-            "metric": "path-traced Mrays/s at 1080p", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "slots_per_gpu_per_pixel": slots_pp, "mode": args.mode,
-                       "l2_policy": "inputs larger than L2 (seed+accumulation state %.1f GB per GPU per step, scene refs ~%d MB)" % (
-                           local * 20 / 1e9, 0), "sm_count": info["sm_count"]},
+                       "l2_policy": "inputs larger than L2: every step streams %.1f GB of per-slot seed+accumulation state and %.1f GB of "
+                                    "per-tile ray/hit state per GPU (L2 = %d MB); no flush needed" % (
+                                        local * 40 / 1e9, local * 116 / 1e9, info["l2_bytes"] >> 20),
+                       "sm_count": info["sm_count"]},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(local * 4 + 64),
                     "d2h_bytes_per_step": int(args.cols * args.rows * 4), "ms_per_step": round(ms_e / args.steps, 3)},
@@ -329,37 +368,39 @@ def main():
     os._exit(0)   # torch's pinned-memory allocator would otherwise record events on the (now destroyed) stream at exit
 
 
-def cpu_baseline(rt, r, scene, args, cam):
+def cpu_rows_default(args, seconds):
+    """Rows of the frame whose CPU pass takes about `seconds` at ~0.6 Mrays/s per host core."""
+    rays_per_row = args.cols * args.spp * (1 + args.depth) * (1 + args.lights) * 0.75
+    rows = int(round(seconds * 0.6e6 * (os.cpu_count() or 8) / rays_per_row))
+    return max(1, min(args.rows, rows))
+
+
+def cpu_baseline(args):
     """Reference kernels on the host cores, on a bounded row sample of the same workload."""
     from oracle import refcl as OR
     olib = OR.load_best()
-    prep = oracle_prep_from_device(rt, r, scene)
-    rows = args.cpu_rows or max(1, min(args.rows, int(round(8 * (1920 * 256) / (args.cols * args.spp)))))
+    scene, prep = oracle_scene(args, tempfile.mkdtemp(prefix="rt_bench_cpu_"))
+    cam = scene["camera"].toFloat32Array()
+    rows = args.cpu_rows or cpu_rows_default(args, 15.0)
     row0 = max(0, args.rows // 2 - rows // 2)
     seeds = make_seeds(args.cols * rows * args.spp, args.seed + 77)
     rays, dt = cpu_pass_rows(olib, prep, cam, args, scene["focal_length"], scene["lens_diameter"], row0, rows, seeds)
     return {"value": round(rays / dt / 1e6, 3), "unit": "Mrays/s", "cores": int(olib.num_threads()), "kind": olib.kind,
-            "sample": "rows %d..%d of %d (all %d slots/px, one pass, %d rays, %.1f s)" % (row0, row0 + rows - 1, args.rows, args.spp, rays, dt)}
+            "sample": "pixel rows %d..%d of %d (all %d slots/px, one executeRender pass, %d rays, %.1f s; reference code.cl kernels "
+                      "compiled by g++ -O2 -fopenmp behind oracle/clshim.h)" % (row0, row0 + rows - 1, args.rows, args.spp, rays, dt)}
 
 
 def main_reference(args, rank):
     """--impl reference: the reference's own kernels (oracle/_ref when compiled, else the C
-    restatement) on the host cores, same scene/metric; each step is a bounded row sample."""
+    restatement) on all host cores, same scene/metric; each step is a bounded row sample.  Nothing
+    of the product (package, library, GPU) is on this path."""
     if rank != 0:
         return
-    rt = importlib.import_module(PKG)
     from oracle import refcl as OR
     olib = OR.load_best()
-    tmp = tempfile.mkdtemp(prefix="rt_bench_ref_")
-    scene = build_scene(rt, args, tmp)
-    # scene buffers: built by the GPU grid build when a GPU is present (same bits as the oracle's split*Data,
-    # tests/test_gpu_a10.py); the timed region contains only the reference's kernels on the CPU.
-    r = rt.Renderer(scene, args.cols, 8, args.spp, depth=args.depth, device=0, mode=1, tile_slots=1 << 16)
-    r.preRender(None)
-    prep = oracle_prep_from_device(rt, r, scene)
-    r.postRender()
+    scene, prep = oracle_scene(args, tempfile.mkdtemp(prefix="rt_bench_ref_"))
     cam = scene["camera"].toFloat32Array()
-    rows = args.cpu_rows or max(1, min(args.rows, int(round(3 * (1920 * 256) / (args.cols * args.spp)))))
+    rows = args.cpu_rows or cpu_rows_default(args, 8.0)
     row0 = max(0, args.rows // 2 - rows // 2)
     rays_t, secs = 0, 0.0
     for i in range(args.warmup + args.steps):
@@ -369,8 +410,9 @@ def main_reference(args, rank):
             rays_t += rays
             secs += dt
     value = rays_t / secs / 1e6
-    sample = "each step = rows %d..%d of %d (all %d slots/px, one pass)" % (row0, row0 + rows - 1, args.rows, args.spp)
-    out = {"impl": "reference", "metric": "path-traced Mrays/s at 1080p", "value": round(value, 3), "unit": "Mrays/s", "n_gpus": args.gpus,
+    sample = ("each step = pixel rows %d..%d of %d (all %d slots/px, one executeRender pass); reference code.cl kernels compiled "
+              "by g++ -O2 -fopenmp behind oracle/clshim.h" % (row0, row0 + rows - 1, args.rows, args.spp))
+    out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 3), "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": workload_name(args)},

@@ -90,6 +90,49 @@ int rt_a10_sceneRender(rt_ctx*, void* acu, void* pois, const void* shadow_rays, 
                        const float* light_info, unsigned total_rays);                                  /* :1323-1364 */
 int rt_a10_copyToPixel(rt_ctx*, void* pixel, const void* acu, float m, unsigned pixels, unsigned rays_per_pixel);   /* :1366-1386 */
 
+/* Earlier assignments (BASELINE.json configs 1-4).  Same conventions; the 2-D NDRange kernels take
+ * the canvas size from the camera (fcam[14], fcam[15]) like the reference kernels do, A08's
+ * `uint2 cols_rows` argument is passed as (cols, rows).  `light_pos` = 4 floats (x,y,z,1), the
+ * Vec3.toFloat32Array of A08/code.js:17-19. */
+int rt_a01_raytrace(rt_ctx*, void* pixels, const float* fcam);                                          /* A01/code.cl:116-147 (fcam packs rows, cols) */
+int rt_a02_raytrace(rt_ctx*, void* pixels, const float* fcam, unsigned s_size, const void* s_atoms,
+                    const void* s_colors);                                                              /* A02/code.cl:158-232 */
+int rt_a03_initTrace(rt_ctx*, void* pixels, const float* fcam, void* rays);                             /* A03/code.cl:132-143 */
+int rt_a03_molTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms,
+                    const void* s_colors);                                                              /* A03/code.cl:145-187 */
+int rt_a07_initTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, const float* bound);         /* A07/code.cl:311-335 */
+int rt_a07_molTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms,
+                    const void* s_mindex, const void* m_color, const float* bound, unsigned n_slabs,
+                    const void* slab_size);                                                             /* A07/code.cl:337-473 */
+int rt_a07_meshTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos,
+                     const void* t_normal, const void* t_mindex, const void* m_color, const float* bound,
+                     unsigned n_slabs, const void* slab_size);                                          /* A07/code.cl:475-626 */
+int rt_a08_initTrace(rt_ctx*, void* acu, void* rays, void* pois, const float* bound, const float* fcam);   /* A08/code.cl:331-363 */
+int rt_a08_initShadowTrace(rt_ctx*, void* shadow_rays, void* pois, unsigned cols, unsigned rows, const float* light_pos);   /* :365-390 */
+int rt_a08_sphereTrace(rt_ctx*, unsigned cols, unsigned rows, void* pois, void* rays, const void* spheres, const void* s_matid,
+                       const void* s_box_size, const float* bound, unsigned n_slabs);                   /* A08/code.cl:392-517 */
+int rt_a08_triangleTrace(rt_ctx*, unsigned cols, unsigned rows, void* pois, void* rays, const void* t_pos, const void* t_normal,
+                         const void* t_matid, const void* t_box_size, const float* bound, unsigned n_slabs);
+int rt_a08_sphereShadowTrace(rt_ctx*, unsigned cols, unsigned rows, void* shadow_rays, const void* spheres, const void* s_box_size,
+                             const float* bound, unsigned n_slabs);
+int rt_a08_triangleShadowTrace(rt_ctx*, unsigned cols, unsigned rows, void* shadow_rays, const void* t_pos, const void* t_box_size,
+                               const float* bound, unsigned n_slabs);
+int rt_a08_sceneRender(rt_ctx*, void* acu, void* pois, const void* shadow_rays, const void* material, unsigned pixels);   /* :916-939 */
+int rt_a08_copyToPixel(rt_ctx*, void* pixel, const void* acu, float m, unsigned pixels);                /* A08/code.cl:941-951 */
+int rt_a09_initTrace(rt_ctx*, void* acu, void* rays, void* pois, const float* bound, const float* fcam, float focal_length,
+                     float lens_rad, unsigned rays_per_pixel);                                          /* A09/code.cl:400-461 */
+int rt_a09_initShadowTrace(rt_ctx*, void* shadow_rays, void* pois, unsigned total_rays, const float* light_pos);   /* A09/code.cl:463-485 */
+int rt_a09_sphereTrace(rt_ctx*, unsigned total_rays, void* pois, void* rays, const void* spheres, const void* s_matid,
+                       const void* s_box_size, const float* bound, unsigned n_slabs);
+int rt_a09_triangleTrace(rt_ctx*, unsigned total_rays, void* pois, void* rays, const void* t_pos, const void* t_normal,
+                         const void* t_matid, const void* t_box_size, const float* bound, unsigned n_slabs);
+int rt_a09_sphereShadowTrace(rt_ctx*, unsigned total_rays, void* shadow_rays, const void* spheres, const void* s_box_size,
+                             const float* bound, unsigned n_slabs);
+int rt_a09_triangleShadowTrace(rt_ctx*, unsigned total_rays, void* shadow_rays, const void* t_pos, const void* t_box_size,
+                               const float* bound, unsigned n_slabs);
+int rt_a09_sceneRender(rt_ctx*, void* acu, void* pois, const void* shadow_rays, const void* material, unsigned total_rays);
+int rt_a09_copyToPixel(rt_ctx*, void* pixel, const void* acu, float m, unsigned pixels, unsigned rays_per_pixel);   /* A09/code.cl:1023-1040 */
+
 /* Optional per-work-item statistics for the five grid-walk launchers (all device pointers,
  * any may be NULL; pass all NULL to switch off): winning reference index (0xFFFFFFFF =
  * none), cells visited, primitive tests.  Used for hit-id parity and for the algorithmic
@@ -193,6 +236,20 @@ int rt_render_stats(rt_render*, unsigned long long* closest_rays, unsigned long 
  * Timing taken with the profile on is not a benchmark number. */
 int rt_render_set_profile(rt_render*, int on);
 int rt_render_read_profile(rt_render*, unsigned long long out[16]);
+/* Same counters per geometry set, in the order the sets were added (row s = set s; [14] is kept in
+ * row 0 only).  rt_render_read_profile returns the column sums. */
+#define RT_MAX_SETS 8
+int rt_render_read_profile_sets(rt_render*, unsigned long long out[RT_MAX_SETS * 16]);
+
+/* Per-kernel-class device time of the executes since timing was switched on (CUDA events on the
+ * context's stream, one in front of every launch): the dominant kernel's average launch duration for
+ * the roofline.  Classes:
+ *   0 per-slot stage kernels (ray generation, small sets, shading)   1 queue walker, spheres, closest hit
+ *   2 queue walker, spheres, any hit    3 queue walker, triangles, closest hit
+ *   4 queue walker, triangles, any hit  5 megakernel   6 reference-schedule kernels   7 sum/copyToPixel */
+#define RT_TIMING_CLASSES 8
+int rt_render_set_timing(rt_render*, int on);
+int rt_render_read_timing(rt_render*, float ms[RT_TIMING_CLASSES], unsigned launches[RT_TIMING_CLASSES]);
 
 #ifdef __cplusplus
 }

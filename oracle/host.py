@@ -235,8 +235,13 @@ def parseMeshJSON(path):
     """A10/tri/meshDataVersion1.js:12-78 with gl-matrix 2.2.1 Float32Array semantics
     (A10/lib/gl-matrix.js:79-80, 1063-1085, 2723-2760): matrices and transformed vectors are
     rounded to fp32 on store; the arithmetic itself is double."""
-    with open(path, "r", encoding="utf-8-sig") as f:
-        model = json.load(f)
+    if isinstance(path, dict):
+        model = path
+        if sum(len(m["vertexPositions"]) for m in model["meshes"]) // 3 >= FAST_MIN_PRIMS:
+            return _parseMeshModel_np(model)
+    else:
+        with open(path, "r", encoding="utf-8-sig") as f:
+            model = json.load(f)
     positions, normals, matidx, materials = [], [], [], []
     b = Bounds()
     nodes = model.get("nodes")
@@ -259,13 +264,15 @@ def parseMeshJSON(path):
                     if v[a] > b.max[a]:
                         b.max[a] = v[a]
             ind = mesh.get("indices")
-            nV = len(ind) if ind else len(vp) // 3
+            if ind is not None and len(ind) == 0:
+                ind = None
+            nV = len(ind) if ind is not None else len(vp) // 3
             nT = nV // 3
             nTriangles += nT
             for i in range(nT):
                 for j in range(3):
                     vi = i * 3 + j
-                    if ind:
+                    if ind is not None:
                         vi = ind[vi]
                     positions.extend(_transformMat4(vp[vi * 3], vp[vi * 3 + 1], vp[vi * 3 + 2], m))
                     normals.extend(_transformMat3(vn[vi * 3], vn[vi * 3 + 1], vn[vi * 3 + 2], nm))
@@ -273,6 +280,48 @@ def parseMeshJSON(path):
     for mat in model["materials"]:
         materials.extend(mat["diffuseReflectance"][:4])
     return {"nTriangles": nTriangles, "nMaterials": len(model["materials"]), "materialIndices": matidx,
+            "materials": materials, "bounds": b, "positions": positions, "normals": normals}
+
+
+def _parseMeshModel_np(model):
+    """Vectorised twin of parseMeshJSON for big in-memory models (same float64 expressions, same
+    fp32 rounding points); tests/test_oracle_host.py checks it against the literal loop."""
+    def r32(a):
+        return np.asarray(a, dtype=np.float64).astype(np.float32).astype(np.float64)
+    pos, nor, mat = [], [], []
+    b = Bounds()
+    nodes = model.get("nodes")
+    for k in range(len(nodes) if nodes else 1):
+        m = [1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0, 0, 0, 0, 0, 1.0]
+        if nodes:
+            m = [_f32(v) for v in nodes[k]["modelMatrix"]]
+        nm = _normalFromMat4(m)
+        for index in (nodes[k]["meshIndices"] if nodes else range(len(model["meshes"]))):
+            mesh = model["meshes"][index]
+            vp = np.asarray(mesh["vertexPositions"], dtype=np.float64).reshape(-1, 3)
+            vn = np.asarray(mesh["vertexNormals"], dtype=np.float64).reshape(-1, 3)
+            x, y, z = vp[:, 0], vp[:, 1], vp[:, 2]
+            tp = r32(np.stack([m[0] * x + m[4] * y + m[8] * z + m[12], m[1] * x + m[5] * y + m[9] * z + m[13],
+                               m[2] * x + m[6] * y + m[10] * z + m[14]], axis=1))
+            x, y, z = vn[:, 0], vn[:, 1], vn[:, 2]
+            tn = r32(np.stack([x * nm[0] + y * nm[3] + z * nm[6], x * nm[1] + y * nm[4] + z * nm[7],
+                               x * nm[2] + y * nm[5] + z * nm[8]], axis=1))
+            if len(tp):
+                for a in range(3):
+                    b.min[a] = min(b.min[a], float(tp[:, a].min()))
+                    b.max[a] = max(b.max[a], float(tp[:, a].max()))
+            ind = mesh.get("indices")
+            idx = np.asarray(ind, dtype=np.int64) if (ind is not None and len(ind)) else np.arange(len(vp), dtype=np.int64)
+            nT = len(idx) // 3
+            idx = idx[:nT * 3]
+            pos.append(tp[idx].reshape(-1))
+            nor.append(tn[idx].reshape(-1))
+            mat.append(np.full(nT, mesh["materialIndex"], dtype=np.int64))
+    positions = np.concatenate(pos) if pos else np.zeros(0)
+    normals = np.concatenate(nor) if nor else np.zeros(0)
+    matidx = np.concatenate(mat) if mat else np.zeros(0, np.int64)
+    materials = [c for mt in model["materials"] for c in mt["diffuseReflectance"][:4]]
+    return {"nTriangles": len(positions) // 9, "nMaterials": len(model["materials"]), "materialIndices": matidx,
             "materials": materials, "bounds": b, "positions": positions, "normals": normals}
 
 
@@ -420,6 +469,51 @@ def _cell_lists(boxes, bmin, bmax, n):
     return np.array(box_size, dtype=np.uint32), np.array(order, dtype=np.int64)
 
 
+FAST_MIN_PRIMS = 20000   # above this the vectorised twins below are used (same results, see tests/test_oracle_host.py)
+
+
+def _cell_lists_np(mn, mx, bmin, bmax, n):
+    """Vectorised twin of _cell_lists for inputs too large for the literal loop: same float64
+    operations per primitive ((v - bmin) / bw, floor, one-sided clamps), pairs generated in
+    primitive order with x fastest, then a STABLE sort by cell -- i.e. input order inside a cell.
+    ``mn``/``mx`` are [N,3] float64.  NaN boxes produce no pairs (JS: the loops are empty)."""
+    mn = np.asarray(mn, dtype=np.float64).reshape(-1, 3)
+    mx = np.asarray(mx, dtype=np.float64).reshape(-1, 3)
+    bmin = np.asarray(bmin, dtype=np.float64)
+    bmax = np.asarray(bmax, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        bw = (bmax - bmin) / float(n)
+        lo = np.floor((mn - bmin) / bw)
+        hi = np.floor((mx - bmin) / bw)
+    bad = np.isnan(lo).any(axis=1) | np.isnan(hi).any(axis=1) | np.isposinf(lo).any(axis=1) | np.isneginf(hi).any(axis=1)
+    lo = np.where(lo < 0, 0.0, lo)
+    hi = np.where(hi >= n, float(n - 1), hi)
+    lo = np.where(np.isneginf(lo), 0.0, lo)
+    hi = np.where(np.isposinf(hi), float(n - 1), hi)
+    lo[bad] = 1.0
+    hi[bad] = 0.0
+    loi = lo.astype(np.int64)
+    ext = np.maximum(hi.astype(np.int64) - loi + 1, 0)
+    cnt = ext[:, 0] * ext[:, 1] * ext[:, 2]
+    total = int(cnt.sum())
+    off = np.concatenate([[0], np.cumsum(cnt)])[:-1]
+    prim = np.repeat(np.arange(len(cnt), dtype=np.int64), cnt)
+    j = np.arange(total, dtype=np.int64) - off[prim]
+    ex, ey = ext[prim, 0], ext[prim, 1]
+    x = loi[prim, 0] + j % np.maximum(ex, 1)
+    y = loi[prim, 1] + (j // np.maximum(ex, 1)) % np.maximum(ey, 1)
+    z = loi[prim, 2] + j // np.maximum(ex * ey, 1)
+    cell = (z * n + y) * n + x
+    order = prim[np.argsort(cell, kind="stable")]
+    box_size = np.concatenate([[0], np.cumsum(np.bincount(cell, minlength=n * n * n))]).astype(np.uint32)
+    return box_size, order
+
+
+def _tri_boxes_np(pos9):
+    p = np.asarray(pos9, dtype=np.float64).reshape(-1, 3, 3)
+    return p.min(axis=1), p.max(axis=1)
+
+
 def _tri_boxes(pos9):
     for i in range(len(pos9) // 9):
         p = pos9[i * 9:i * 9 + 9]
@@ -442,7 +536,10 @@ def splitMeshData(meshData, nn_slabs):
     material index).  Returns posData, normalData (float64, before any Mesh transform),
     boxSizeData, indexData."""
     b = meshData["bounds"]
-    box_size, order = _cell_lists(_tri_boxes(meshData["positions"]), b.min, b.max, nn_slabs)
+    if len(meshData["positions"]) // 9 >= FAST_MIN_PRIMS:
+        box_size, order = _cell_lists_np(*_tri_boxes_np(meshData["positions"]), b.min, b.max, nn_slabs)
+    else:
+        box_size, order = _cell_lists(_tri_boxes(meshData["positions"]), b.min, b.max, nn_slabs)
     idx = np.asarray(meshData["materialIndices"], dtype=np.uint32)[order] if len(order) else np.zeros(0, np.uint32)
     return _gather_tri(meshData["positions"], order), _gather_tri(meshData["normals"], order), box_size, idx
 

@@ -259,3 +259,171 @@ def a10_render(lib, scene, cols, rows, rpp, passes=1, seeds=None, seed=2015, n_s
     for _ in range(passes):
         pixel = a10_execute_render(lib, st, prep, cam16, cols, rows, rpp, scene["focal_length"], scene["lens_diameter"], depth)
     return st, pixel, prep
+
+
+# ===================================================================================
+# Frame schedules of the earlier assignments (BASELINE.json configs 1-4)
+# ===================================================================================
+def a01_render(lib, cols, rows):
+    """A01/code.js:166-269 (compute): constant camera, one `raytrace` launch."""
+    pix = np.zeros((rows * cols, 4), dtype=np.uint8)
+    lib.a01_raytrace(pix, H.camera_a01(cols, rows), cols, rows)
+    return pix.reshape(rows, cols, 4)
+
+
+def pack_atoms(molData):
+    """A03/code.js:524-537: Float32Array(size*4) atom (x,y,z,radius) and colour records; records
+    past the end of atomData read `undefined` and become NaN (Q13)."""
+    n = int(molData["size"])
+    ad = np.asarray(molData["atomData"], dtype=np.float64).reshape(-1, 4)
+    rd = np.asarray(molData["radiusData"], dtype=np.float64)
+    cd = np.asarray(molData["colorData"], dtype=np.float64).reshape(-1, 4)
+    atoms = np.full((n, 4), np.nan)
+    colors = np.full((n, 4), np.nan)
+    m = min(n, len(ad))
+    ids = ad[:m, 0].astype(np.int64)
+    atoms[:m, :3] = ad[:m, 1:4]
+    atoms[:m, 3] = rd[ids]
+    colors[:m] = cd[ids]
+    return H.to_f32(atoms.reshape(-1)), H.to_f32(colors.reshape(-1))
+
+
+def mol_camera(bounds, cols, rows):
+    """cam.defaultInit(); cam.set(bounds, width, height) -- A03/code.js:55-70,113-118,
+    A07/code.js:45-124."""
+    cam = H.Camera()
+    cam.defaultInit()
+    cam.set(bounds, cols, rows)
+    return cam
+
+
+def a02_render(lib, molData, cols, rows):
+    """A02/code.js:413-573: one fused `raytrace` launch over all atoms."""
+    atoms, colors = pack_atoms(molData)
+    cam16 = mol_camera(molData["bounds"], cols, rows).toFloat32Array()
+    pix = np.zeros((rows * cols, 4), dtype=np.uint8)
+    lib.a02_raytrace(pix, cam16, int(molData["size"]), atoms, colors, cols, rows)
+    return pix.reshape(rows, cols, 4)
+
+
+def a03_render(lib, molData, cols, rows):
+    """A03/code.js:450-598: `initTrace` then `molTrace`.  Returns (pixels, rays)."""
+    atoms, colors = pack_atoms(molData)
+    cam16 = mol_camera(molData["bounds"], cols, rows).toFloat32Array()
+    pix = np.zeros((rows * cols, 4), dtype=np.uint8)
+    rays = np.zeros(rows * cols, dtype=RAY)
+    lib.a03_initTrace(pix, cam16, rays, cols, rows)
+    lib.a03_molTrace(pix, cam16, rays, int(molData["size"]), atoms, colors, cols, rows)
+    return pix.reshape(rows, cols, 4), rays
+
+
+def prepare_a07_mol(molData, n_slabs):
+    """prepareMolTrace, A07/code.js:434-483."""
+    pos, idx, box = H.splitMolData(molData, n_slabs)
+    return {"size": int(molData["size"]), "atoms": H.to_f32(pos), "index": np.asarray(idx, dtype=np.uint32),
+            "colors": H.to_f32(molData["colorData"]), "box": np.asarray(box, dtype=np.uint32),
+            "aabb": H.bounds2AABB(molData["bounds"]), "n": int(n_slabs)}
+
+
+def prepare_a07_mesh(meshData, n_slabs):
+    """prepareMeshTrace, A07/code.js:485-542."""
+    pos, nor, box, idx = H.splitMeshData(meshData, n_slabs)
+    return {"size": int(meshData["nTriangles"]), "pos": H.to_f32(pos), "normal": H.to_f32(nor),
+            "index": np.asarray(idx, dtype=np.uint32), "colors": H.to_f32(meshData["materials"]),
+            "box": np.asarray(box, dtype=np.uint32), "aabb": H.bounds2AABB(meshData["bounds"]), "n": int(n_slabs)}
+
+
+def a07_render(lib, cols, rows, n_slabs=2, molData=None, meshData=None):
+    """compute / computeTri / computeBoth, A07/code.js:571-668: `initTrace` against the (merged)
+    bounds, then `molTrace` and/or `meshTrace` over the same ray buffer.  Returns
+    (pixels, rays, prep)."""
+    bounds = H.Bounds()
+    if molData is not None and meshData is not None:
+        bounds.merge(molData["bounds"])
+        bounds.merge(meshData["bounds"])
+    else:
+        bounds = (molData or meshData)["bounds"]
+    cam16 = mol_camera(bounds, cols, rows).toFloat32Array()
+    pix = np.zeros((rows * cols, 4), dtype=np.uint8)
+    rays = np.zeros(rows * cols, dtype=RAY)
+    lib.a07_initTrace(pix, cam16, rays, H.bounds2AABB(bounds), cols, rows)
+    prep = {"cam": cam16, "aabb": H.bounds2AABB(bounds)}
+    if molData is not None:
+        m = prep["mol"] = prepare_a07_mol(molData, n_slabs)
+        lib.a07_molTrace(pix, cam16, rays, m["size"], m["atoms"], m["index"], m["colors"], m["aabb"], m["n"], m["box"], cols, rows)
+    if meshData is not None:
+        t = prep["mesh"] = prepare_a07_mesh(meshData, n_slabs)
+        lib.a07_meshTrace(pix, cam16, rays, t["size"], t["pos"], t["normal"], t["index"], t["colors"], t["aabb"], t["n"], t["box"],
+                          cols, rows)
+    return pix.reshape(rows, cols, 4), rays, prep
+
+
+def prepare_a089(scene, n_slabs=5):
+    """prepareSphereTrace / prepareTriangleTrace of A08/A09 (A08/code.js:684-775)."""
+    out = {"aabb": H.bounds2AABB(scene["bounds"]), "materials": H.splitMaterialData(scene), "n": int(n_slabs),
+           "sphere": None, "triangle": None,
+           "lights": [np.array([L.x, L.y, L.z, 1.0], dtype=np.float64).astype(np.float32) for L in scene["lights"]]}
+    if len(scene["spheres"]) > 0:
+        data, mat, box = H.splitSphereData(scene, n_slabs)
+        out["sphere"] = {"data": H.to_f32(data), "matid": mat.astype(np.uint32), "box": box, "aabb": H.bounds2AABB(scene["sphereBounds"])}
+    if len(scene["triangles"]) > 0:
+        pos, nor, mat, box = H.splitTriangleData(scene, n_slabs)
+        out["triangle"] = {"pos": H.to_f32(pos), "normal": H.to_f32(nor), "matid": mat.astype(np.uint32), "box": box,
+                           "aabb": H.bounds2AABB(scene["triangleBounds"])}
+    return out
+
+
+def a08_render(lib, scene, cols, rows, n_slabs=5):
+    """render(), A08/code.js:1194-1232: one ray per pixel, point lights, 2-D NDRange.  Quirk Q10:
+    triangleShadowTrace is handed the SPHERE bounds (A08/code.js:918).  Returns (acu, pixels, state)."""
+    prep = prepare_a089(scene, n_slabs)
+    n = cols * rows
+    st = {"rays": np.zeros(n, dtype=RAY), "pois": np.zeros(n, dtype=POI8), "shadow": np.zeros(n, dtype=RAY),
+          "acu": np.zeros((n, 4), dtype=np.float32)}
+    cam16 = scene["camera"].toFloat32Array()
+    S, T, N = prep["sphere"], prep["triangle"], prep["n"]
+    lib.a08_initTrace(st["acu"], st["rays"], st["pois"], prep["aabb"], cam16, cols, rows)
+    if S:
+        lib.a08_sphereTrace(cols, rows, st["pois"], st["rays"], S["data"], S["matid"], S["box"], S["aabb"], N)
+    if T:
+        lib.a08_triangleTrace(cols, rows, st["pois"], st["rays"], T["pos"], T["normal"], T["matid"], T["box"], T["aabb"], N)
+    sphere_aabb = H.bounds2AABB(scene["sphereBounds"])
+    for L in prep["lights"]:
+        lib.a08_initShadowTrace(st["shadow"], st["pois"], cols, rows, L)
+        if S:
+            lib.a08_sphereShadowTrace(cols, rows, st["shadow"], S["data"], S["box"], S["aabb"], N)
+        if T:
+            lib.a08_triangleShadowTrace(cols, rows, st["shadow"], T["pos"], T["box"], sphere_aabb, N)
+        lib.a08_sceneRender(st["acu"], st["pois"], st["shadow"], prep["materials"], n)
+    pix = np.zeros((n, 4), dtype=np.uint8)
+    lib.a08_copyToPixel(pix, st["acu"], float(np.float32(1.0 / len(prep["lights"]))), n)
+    return st["acu"], pix.reshape(rows, cols, 4), st
+
+
+def a09_render(lib, scene, cols, rows, rays_per_pixel, n_slabs=5, focal_length=None, lens_diameter=None):
+    """render(), A09/code.js:1256-1294: thin-lens stratified primaries, 1-D NDRange over
+    total_rays.  Returns (acu [total,4], pixels, state)."""
+    prep = prepare_a089(scene, n_slabs)
+    total = cols * rows * rays_per_pixel
+    st = {"rays": np.zeros(total, dtype=RAY), "pois": np.zeros(total, dtype=POI8), "shadow": np.zeros(total, dtype=RAY),
+          "acu": np.zeros((total, 4), dtype=np.float32)}
+    cam16 = scene["camera"].toFloat32Array()
+    fl = scene["focal_length"] if focal_length is None else focal_length
+    ld = scene["lens_diameter"] if lens_diameter is None else lens_diameter
+    S, T, N = prep["sphere"], prep["triangle"], prep["n"]
+    lib.a09_initTrace(st["acu"], st["rays"], st["pois"], prep["aabb"], cam16, float(np.float32(fl)), float(np.float32(ld / 2.0)),
+                      rays_per_pixel, cols, rows)
+    if S:
+        lib.a09_sphereTrace(total, st["pois"], st["rays"], S["data"], S["matid"], S["box"], S["aabb"], N)
+    if T:
+        lib.a09_triangleTrace(total, st["pois"], st["rays"], T["pos"], T["normal"], T["matid"], T["box"], T["aabb"], N)
+    for L in prep["lights"]:
+        lib.a09_initShadowTrace(st["shadow"], st["pois"], total, L)
+        if S:
+            lib.a09_sphereShadowTrace(total, st["shadow"], S["data"], S["box"], S["aabb"], N)
+        if T:
+            lib.a09_triangleShadowTrace(total, st["shadow"], T["pos"], T["box"], T["aabb"], N)
+        lib.a09_sceneRender(st["acu"], st["pois"], st["shadow"], prep["materials"], total)
+    pix = np.zeros((cols * rows, 4), dtype=np.uint8)
+    lib.a09_copyToPixel(pix, st["acu"], float(np.float32(1.0 / (rays_per_pixel * len(prep["lights"])))), cols * rows, rays_per_pixel)
+    return st["acu"], pix.reshape(rows, cols, 4), st

@@ -1,0 +1,132 @@
+"""CPU tests (no GPU): the oracle -- the reference's kernels compiled from where they lie
+(oracle/_ref) or the plain-C restatement, driven by the JS-order host restatement -- must
+reproduce every golden fixture under tests/golden/ bit for bit.  The fixtures were produced by
+tests/golden/make_golden.py from the reference's own demo inputs; this pins the oracle build
+(compiler, flags, OpenMP schedule independence) on whatever machine runs the parity tests."""
+import numpy as np
+import pytest
+
+import golden_io as G
+from oracle import host as OH
+from oracle import refcl as OR
+
+
+def _eq(a, b, what):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert a.shape == b.shape, what
+    assert a.tobytes() == b.tobytes(), what + ": differs from the golden fixture"
+
+
+@pytest.mark.parametrize("name", G.names("a10_"))
+def test_a10_scene(oracle_lib, tmp_path, name):
+    fx = G.load(name)
+    P = fx["params"]
+    path = G.materialize_scene(fx["tree"], G.meshes_of(fx), tmp_path)
+    scene = OH.loadScene(path, P["cols"], P["rows"], assignment=10)
+    _eq(scene["camera"].toFloat32Array(), fx["cam16"], "camera float16")
+    prep = OR.prepare_a10(scene, 1)
+    for s, g in zip(prep["sets"], fx["grids"]):
+        assert int(s["box"][-1]) == g["refs"] and G.digest(s["box"].astype(np.uint32)) == g["box"]
+        assert G.digest(s["data"] if s["kind"] == "sphere" else s["pos"]) == g["prim"]
+    total = P["cols"] * P["rows"] * P["rpp"]
+    st = OR.A10State(total, OR.make_seeds(total, P["seed"]))
+    oracle_lib.a10_initAcu(st.acu, total)
+    for p in range(P["passes"]):
+        pix = OR.a10_execute_render(oracle_lib, st, prep, fx["cam16"], P["cols"], P["rows"], P["rpp"], scene["focal_length"],
+                                    scene["lens_diameter"])
+        acc = np.zeros((P["cols"] * P["rows"], 4), np.float32)
+        for k in range(P["rpp"]):
+            acc += st.acu.reshape(-1, P["rpp"], 4)[:, k]
+        _eq(acc, fx["accum"][p], "accumulation image, pass %d" % p)
+        _eq(st.seeds, fx["seeds_after"][p], "seed buffer after pass %d" % p)
+        _eq(pix, fx["pixels"][p], "pixels, pass %d" % p)
+        assert [st.n_closest, st.n_any] == list(fx["counts"][p])
+
+
+@pytest.mark.parametrize("name", G.names("a08_") + G.names("a09_"))
+def test_a08_a09_scene(oracle_lib, tmp_path, name):
+    fx = G.load(name)
+    P = fx["params"]
+    path = G.materialize_scene(fx["tree"], [], tmp_path)
+    scene = OH.loadScene(path, P["cols"], P["rows"], assignment=P["assignment"])
+    if P["assignment"] == 8:
+        acu, pix, st = OR.a08_render(oracle_lib, scene, P["cols"], P["rows"], P["n_slabs"])
+    else:
+        acu, pix, st = OR.a09_render(oracle_lib, scene, P["cols"], P["rows"], P["rpp"], P["n_slabs"])
+    _eq(acu, fx["acu"], "acu")
+    _eq(pix, fx["pixels"], "pixels")
+    _eq(st["pois"]["matId"].astype(np.int32), fx["matid"], "hit material ids")
+    _eq(st["rays"]["maxt"], fx["maxt"], "ray maxt")
+
+
+@pytest.mark.parametrize("name", G.names("mol_"))
+def test_molecule(oracle_lib, name):
+    fx = G.load(name)
+    P = fx["params"]
+    mol = OH.parsePDB(G.pdb_text(fx["serial"], fx["elem"], fx["xyz"]))
+    assert mol["size"] == P["size"]
+    _eq(OR.a02_render(oracle_lib, mol, P["cols"], P["rows"]), fx["a02_pixels"], "A02 pixels")
+    p3, r3 = OR.a03_render(oracle_lib, mol, P["cols"], P["rows"])
+    _eq(p3, fx["a03_pixels"], "A03 pixels")
+    _eq(r3["mint"], fx["a03_mint"], "A03 ray mint")
+    for n, g in zip(P["slabs"], fx["grids"]):
+        p7, r7, prep = OR.a07_render(oracle_lib, P["cols"], P["rows"], n, molData=mol)
+        m = prep["mol"]
+        assert (int(m["box"][-1]), G.digest(m["box"]), G.digest(m["atoms"]), G.digest(m["index"])) == (g["refs"], g["box"], g["prim"], g["index"])
+        _eq(p7, fx["a07_pixels_n%d" % n], "A07 molTrace pixels n=%d" % n)
+        _eq(r7["maxt"], fx["a07_maxt_n%d" % n], "A07 molTrace maxt n=%d" % n)
+
+
+@pytest.mark.parametrize("name", G.names("tri_"))
+def test_mesh(oracle_lib, tmp_path, name):
+    fx = G.load(name)
+    P = fx["params"]
+    m = G.meshes_of(fx)[0]
+    p = tmp_path / "m.json"
+    p.write_text(G.mesh_json_text(m["positions"], m["normals"], m["materialIndices"], m["materials"]))
+    md = OH.parseMeshJSON(str(p))
+    assert np.array_equal(np.asarray(md["positions"]), m["positions"])
+    for g in fx["grids"]:
+        pos, nor, box, idx = OH.splitMeshData(md, g["n"])
+        assert (int(box[-1]), G.digest(box.astype(np.uint32)), G.digest(OH.to_f32(pos)), G.digest(OH.to_f32(nor))) == (
+            g["refs"], g["box"], g["prim"], g["normal"])
+    for n in P["slabs"]:
+        p7, r7, _ = OR.a07_render(oracle_lib, P["cols"], P["rows"], n, meshData=md)
+        _eq(p7, fx["a07_pixels_n%d" % n], "A07 meshTrace pixels n=%d" % n)
+        _eq(r7["maxt"], fx["a07_maxt_n%d" % n], "A07 meshTrace maxt n=%d" % n)
+    if P.get("with_mol"):
+        mol = OH.parsePDB(G.pdb_text(fx["both_serial"], fx["both_elem"], fx["both_xyz"]))
+        pb, rb, _ = OR.a07_render(oracle_lib, P["cols"], P["rows"], 5, molData=mol, meshData=md)
+        _eq(pb, fx["both_pixels"], "A07 computeBoth pixels")
+        _eq(rb["maxt"], fx["both_maxt"], "A07 computeBoth maxt")
+
+
+def test_a01(oracle_lib):
+    fx = G.load("a01")
+    for cols, rows in fx["params"]["sizes"]:
+        _eq(OR.a01_render(oracle_lib, cols, rows), fx["pixels_%dx%d" % (cols, rows)], "A01 %dx%d" % (cols, rows))
+
+
+def test_struct_size_probes(oracle_lib):
+    """sizeofRay / sizeofPoi (A10/code.cl:440-446): the layouts every buffer is sized by."""
+    assert oracle_lib.a10_sizeofRay() == 48 and oracle_lib.a10_sizeofPoi() == 64
+    assert oracle_lib.a08_sizeofRay() == 48 and oracle_lib.a08_sizeofPoi() == 48
+    assert oracle_lib.a09_sizeofRay() == 48 and oracle_lib.a09_sizeofPoi() == 48
+    assert oracle_lib.a03_sizeofRay() == 48 and oracle_lib.a07_sizeofRay() == 48
+
+
+def test_instrumented_build_is_arithmetic_neutral(tmp_path):
+    """The counting hooks of libref_instr.so sit at non-arithmetic places: same buffers as libref.so."""
+    if not OR.have_reference():
+        pytest.skip("oracle/_ref not built")
+    fx = G.load("a10_cornell_teapot3")
+    P = fx["params"]
+    scene = OH.loadScene(G.materialize_scene(fx["tree"], G.meshes_of(fx), tmp_path), P["cols"], P["rows"])
+    res = []
+    for instr in (False, True):
+        lib = OR.load_reference(instrumented=instr)
+        assert lib.instrumented == instr
+        st, pix, _ = OR.a10_render(lib, scene, P["cols"], P["rows"], P["rpp"], passes=1, seed=P["seed"])
+        res.append((st.acu.copy(), st.seeds.copy(), pix.copy()))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
