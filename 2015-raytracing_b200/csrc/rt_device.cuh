@@ -279,6 +279,30 @@ RT_DEV bool interTrianglePre(f3 o, f3 d, float mint, float maxt, float div, f3 p
     return true;
 }
 
+// The same test once more, arranged for throughput: the two cheap sign rejections come BEFORE the
+// IEEE division.  Equivalent decisions and identical floats: with div > 0 the reciprocal idiv is in
+// (0, +inf], so beta = nb * idiv < 0  <=>  nb < 0 and gamma = ngm * idiv < 0  <=>  ngm < 0 (a NaN
+// numerator fails both comparisons on either route; div = +inf, where idiv = 0 would turn a negative
+// numerator into -0, is excluded by the guard).  Rejections have no side effects, so their order is free.
+RT_DEV bool interTriangleFast(f3 o, f3 d, float mint, float maxt, float div, f3 p0, f3 e1, f3 e2, float& beta_o, float& gamma_o, float& t_out) {
+    if (div <= 0) return false;
+    f3 s = o - p0;
+    float nb = dot(cross(s, d), e2);
+    float ngm = dot(cross(s, e1), d);
+    if ((nb < 0.0f || ngm < 0.0f) && div < RT_INF) return false;
+    float idiv = 1.0f / div;
+    float beta = nb * idiv;
+    if (beta < 0.0f || beta > 1.0f) return false;
+    float gamma = ngm * idiv;
+    if (gamma < 0.0f || (gamma + beta) < 0.0f || (gamma + beta) > 1.0f) return false;
+    float t = dot(cross(s, e2), e1) * -idiv;
+    if (!(t >= mint && t <= maxt)) return false;
+    beta_o = beta;
+    gamma_o = gamma;
+    t_out = t;
+    return true;
+}
+
 // A10/code.cl:391-403 (no t > 0 test -- quirk Q5).
 RT_DEV bool interLight(f3 o, f3 d, f3 light_pos, f3 light_normal, float radius, float& t_out) {
     float den = dot(d, light_normal);
@@ -539,6 +563,57 @@ RT_DEV Hit gridWalk(f3 o, f3 d, float maxt_in, const GridView& g, const AabbHit&
     walkInit(w, PRIM, o, d, maxt_in, g, binter);
     while (!walkCell<PRIM, ANY, TRI_INCL, STATS, OCC>(w, g, st)) {}
     return w.h;
+}
+
+// Walk over a ONE-cell grid (n_slabs == 1: every XML sphere/triangle set of Assignment 10, whose global
+// n_slabs is 1, A10/code.js:399).  Same floats as gridWalk: with n = 1 the entry slab clamps to 0 whatever
+// (int)((x - pmin) / delta) is, the cell interval is [binter.tmin, min(t_next)] with
+// t_next = (pmin + (d >= 0 ? 1 : 0) * delta - o) / d, delta = (pmax - pmin) / 1.0f, and after the cell the
+// first step always reaches slab == limit (A10/code.cl:770-785), so the loop body runs exactly once.
+// Triangles come in the precomputed form (face vector, p0, e1, e2 -- f_precomputeTriangles).
+template <int PRIM, bool ANY, bool STATS>
+RT_DEV Hit singleCellWalk(f3 o, f3 d, float maxt_in, const GridView& g, const float4* __restrict__ pre_ng, const float4* __restrict__ pre_pe,
+                          const AabbHit& binter, WalkStats* st) {
+    Hit h;
+    h.t = maxt_in;
+    h.i = 0xFFFFFFFFu;
+    h.beta = 0.f; h.gamma = 0.f;
+    h.cx = h.cy = h.cz = 1;
+    const float dx = (g.bound.pmax.x - g.bound.pmin.x) / 1.0f, dy = (g.bound.pmax.y - g.bound.pmin.y) / 1.0f,
+                dz = (g.bound.pmax.z - g.bound.pmin.z) / 1.0f;
+    const float tx = ((g.bound.pmin.x + (float)((d.x >= 0) ? 1 : 0) * dx) - o.x) / d.x;
+    const float ty = ((g.bound.pmin.y + (float)((d.y >= 0) ? 1 : 0) * dy) - o.y) / d.y;
+    const float tz = ((g.bound.pmin.z + (float)((d.z >= 0) ? 1 : 0) * dz) - o.z) / d.z;
+    const float mint = binter.tmin;
+    const float maxt = cl_min(cl_min(tx, ty), tz);
+    const unsigned begin = __ldg(g.box), end = __ldg(g.box + 1);
+    const float a_dd = (PRIM == PRIM_SPHERE) ? dot(d, d) : 0.f;
+    if (STATS) st->cells++;
+    for (unsigned i = begin; i < end; i++) {
+        float ti, be = 0.f, ga = 0.f;
+        bool v;
+        if (PRIM == PRIM_SPHERE) {
+            v = interSphere(o, d, a_dd, mint, maxt, __ldg(g.prim + i), ti);
+        } else {
+            float4 q = __ldg(pre_ng + i);
+            float div = dot(mk3(q.x, q.y, q.z), d);
+            v = false;
+            if (div > 0) {
+                float4 q0 = __ldg(pre_pe + 3 * i), q1 = __ldg(pre_pe + 3 * i + 1), q2 = __ldg(pre_pe + 3 * i + 2);
+                v = interTriangleFast(o, d, mint, maxt, div, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
+            }
+        }
+        if (STATS) st->tests++;
+        if (v && ti < h.t) {
+            h.t = ti;
+            h.i = i;
+            h.beta = be;
+            h.gamma = ga;
+            h.cx = h.cy = h.cz = 0;
+            if (ANY) break;
+        }
+    }
+    return h;
 }
 
 // ---------------------------------------------------------------------------------------

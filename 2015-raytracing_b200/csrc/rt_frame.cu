@@ -272,7 +272,7 @@ int rt_scene_add_set(rt_scene* s, const rt_grid* grid, const float bound[8], int
                                                                                                  st.macro_n, st.macro_occ);
         RT_LAUNCH_CHECK(ctx, "macroOccupancy");
     }
-    if (grid->kind == 1 && grid->n_slabs > 2 && grid->n_refs > 64 && grid->occupancy) {   // "heavy" triangle set, see rt_wavefront.cu
+    if (grid->kind == 1 && grid->n_refs > 0) {   // every triangle set: precomputed face vector / edges (queue walkers and 1-cell sets)
         rt_ctx* ctx = s->ctx;
         RT_TRY(rt_buffer_create(ctx, sizeof(float4) * grid->n_refs, (void**)&st.pre_ng));
         RT_TRY(rt_buffer_create(ctx, sizeof(float4) * 3 * (size_t)grid->n_refs, (void**)&st.pre_pe));
@@ -311,9 +311,11 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     r->pixels = (size_t)r->o.cols * r->o.rows;
     r->local_slots = r->pixels * r->slots_pp;
     if ((unsigned long long)r->pixels * r->o.rays_per_pixel > 0xFFFFFFFFull) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: total_rays exceeds the reference's uint range"); }
-    // default tile: 4 Mi slots -- large enough that every lane of the persistent queue walkers pops
-    // several tasks (their load balancing needs a deep queue); state ~116 B/slot streams through HBM
-    size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)1 << 22;
+    // default tile: as many slots as a quarter of the device memory holds (116 B of wavefront state per slot,
+    // 180 GB of HBM3e on B200 -> ~390 Mi slots): the persistent queue walkers need a DEEP queue -- with 4 Mi-slot
+    // tiles a walk launch got ~0.5 M rays for 151 k lanes and spent a quarter of its time in the drain tail
+    size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)(ctx->prop.totalGlobalMem / 4 / 116);
+    if (want < ((size_t)1 << 22)) want = (size_t)1 << 22;
     size_t px_per_tile = want / r->slots_pp;
     if (px_per_tile == 0) px_per_tile = 1;
     if (px_per_tile > r->pixels) px_per_tile = r->pixels;

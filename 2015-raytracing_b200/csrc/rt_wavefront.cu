@@ -65,7 +65,10 @@ RT_DEV void closestSet(const SetDev& s, RayR& ray, PoiR& poi, unsigned* prof) {
     if (!binter.v) return;
     Hit h;
     WalkStats ws = {0, 0};
-    if (s.kind == PRIM_SPHERE) h = gridWalk<PRIM_SPHERE, false, true, STATS, OCC>(ray.o, ray.d, ray.maxt, s.g, binter, &ws);
+    if (s.g.n == 1 && (s.kind == PRIM_SPHERE || s.pre_ng)) {
+        if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, false, STATS>(ray.o, ray.d, ray.maxt, s.g, nullptr, nullptr, binter, &ws);
+        else h = singleCellWalk<PRIM_TRIANGLE, false, STATS>(ray.o, ray.d, ray.maxt, s.g, s.pre_ng, s.pre_pe, binter, &ws);
+    } else if (s.kind == PRIM_SPHERE) h = gridWalk<PRIM_SPHERE, false, true, STATS, OCC>(ray.o, ray.d, ray.maxt, s.g, binter, &ws);
     else h = gridWalk<PRIM_TRIANGLE, false, true, STATS, OCC>(ray.o, ray.d, ray.maxt, s.g, binter, &ws);
     if (STATS) {
         prof[1]++;
@@ -96,7 +99,10 @@ RT_DEV void anySet(const SetDev& s, RayR& sr, unsigned* prof) {
     if (!binter.v) return;
     Hit h;
     WalkStats ws = {0, 0};
-    if (s.kind == PRIM_SPHERE) h = gridWalk<PRIM_SPHERE, true, true, STATS, OCC>(sr.o, sr.d, sr.maxt, s.g, binter, &ws);
+    if (s.g.n == 1 && (s.kind == PRIM_SPHERE || s.pre_ng)) {
+        if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, true, STATS>(sr.o, sr.d, sr.maxt, s.g, nullptr, nullptr, binter, &ws);
+        else h = singleCellWalk<PRIM_TRIANGLE, true, STATS>(sr.o, sr.d, sr.maxt, s.g, s.pre_ng, s.pre_pe, binter, &ws);
+    } else if (s.kind == PRIM_SPHERE) h = gridWalk<PRIM_SPHERE, true, true, STATS, OCC>(sr.o, sr.d, sr.maxt, s.g, binter, &ws);
     else h = gridWalk<PRIM_TRIANGLE, true, true, STATS, OCC>(sr.o, sr.d, sr.maxt, s.g, binter, &ws);
     if (STATS) {
         prof[9]++;
@@ -325,7 +331,10 @@ RT_DEV void pushTask(bool want, unsigned id, unsigned* queue, unsigned* count) {
     if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = id;
 }
 
-__global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SceneDev sc, const __grid_constant__ PathArgs a,
+#ifndef RT_STAGE_MINB
+#define RT_STAGE_MINB 4
+#endif
+__global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_constant__ SceneDev sc, const __grid_constant__ PathArgs a,
                                                const __grid_constant__ WaveState w, const __grid_constant__ StageOp op) {
     unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     bool inb = id < a.n_local;
@@ -726,7 +735,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_coop(c
                         r = s_cand[wid][j];
                         float dv = s_div[wid][j];
                         float4 q0 = __ldg(set.pre_pe + 3 * r), q1 = __ldg(set.pre_pe + 3 * r + 1), q2 = __ldg(set.pre_pe + 3 * r + 2);
-                        v = interTrianglePre(o, d, mint, maxt, dv, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
+                        v = interTriangleFast(o, d, mint, maxt, dv, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
                     } else {
                         r = base + j;
                         float4 sp = __ldg(g.prim + r);
@@ -756,6 +765,220 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_coop(c
             }
             if ((int)lane == L) f.i = f.end;   // cell done; flatLeave ends the walk if it produced the hit
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Pair-list queue walker (default).  Same outer structure as k_walk_coop -- every lane owns one ray
+// and steps its own DDA through empty cells -- but the primitive tests of ALL lanes that stand in
+// a non-empty cell are done together: the (owner lane, reference) pairs of those cells are laid
+// out as one list (warp prefix sum of the cell populations), and the warp walks that list 32
+// pairs at a time, so the face-vector cull runs on dense lanes whatever the cell populations
+// are (a cell holds ~7 references on the 1 M-triangle mesh, which left k_walk_coop's 32-wide
+// per-cell passes 3/4 empty).  Survivors are compacted into a candidate buffer and the full
+// test again runs 32 candidates at a time.  Each lane fetches its pair's ray from the owner lane
+// with indexed shuffles.  Accepted hits (rare) are reduced per owner with one shared-memory
+// atomicMin on the key (t bits, reference index) [closest: min t, ties -> lowest index] or
+// (reference index) [any hit: first accepted reference in list order] -- exactly the winner of
+// the reference's sequential loop (A10/code.cl:882-897, 1272-1287), whose floats the owner then
+// recomputes with one more test of the winning reference.
+// ---------------------------------------------------------------------------------------
+constexpr int kCandCap = 64;
+
+template <int PRIM, bool ANY>
+__global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w,
+                                                                               unsigned n, int qslot) {
+    __shared__ unsigned s_macro[8192];   // 64^3 bits
+    __shared__ unsigned s_off[kWalkWarps][32];
+    __shared__ unsigned s_cref[kWalkWarps][kCandCap];
+    __shared__ unsigned s_cown[kWalkWarps][kCandCap];
+    __shared__ float s_cdiv[kWalkWarps][kCandCap];
+    __shared__ unsigned long long s_best[kWalkWarps][32];
+    for (unsigned i = threadIdx.x; i < 8192; i += blockDim.x) s_macro[i] = set.macro_occ[i];
+    __syncthreads();
+    const unsigned mshift = set.macro_shift, mn = set.macro_n;
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned long long NONE = ~0ull;
+    const unsigned count = w.qctr[2 * qslot];
+    unsigned* head = w.qctr + 2 * qslot + 1;
+    const float4* src = ANY ? w.sh : w.ray;
+    const GridView& g = set.g;
+    FlatWalker f;
+    f.i = f.end = 0;
+    unsigned slot = 0;
+    bool have = false;
+    bool drained = false;
+
+    // full test of candidates [0, cnt) of the buffer, one per lane; accepted hits go to s_best[owner]
+    auto testCandidates = [&](unsigned cnt) {
+        const bool act = lane < cnt;
+        unsigned r = 0, own = lane;
+        float dv = 0.f;
+        if (act) { r = s_cref[wid][lane]; own = s_cown[wid][lane]; dv = s_cdiv[wid][lane]; }
+        const f3 o = mk3(__shfl_sync(FULL, f.w.o.x, own), __shfl_sync(FULL, f.w.o.y, own), __shfl_sync(FULL, f.w.o.z, own));
+        const f3 d = mk3(__shfl_sync(FULL, f.w.d.x, own), __shfl_sync(FULL, f.w.d.y, own), __shfl_sync(FULL, f.w.d.z, own));
+        const float mint = __shfl_sync(FULL, f.mint, own), maxt = __shfl_sync(FULL, f.maxt, own);
+        const float champ = __shfl_sync(FULL, f.w.h.t, own);
+        const float a_dd = (PRIM == PRIM_SPHERE) ? __shfl_sync(FULL, f.w.a_dd, own) : 0.f;
+        if (act) {
+            float ti, be, ga;
+            bool v;
+            if (PRIM == PRIM_TRIANGLE) {
+                float4 q0 = __ldg(set.pre_pe + 3 * r), q1 = __ldg(set.pre_pe + 3 * r + 1), q2 = __ldg(set.pre_pe + 3 * r + 2);
+                v = interTriangleFast(o, d, mint, maxt, dv, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
+            } else {
+                v = interSphere(o, d, a_dd, mint, maxt, __ldg(g.prim + r), ti);
+            }
+            if (v && ti < champ) {
+                // accepted t >= mint >= 0 (interAABB clamps tmin at 0), so the bit pattern of t + 0.0f orders like t
+                unsigned long long key = ANY ? (unsigned long long)r : (((unsigned long long)__float_as_uint(ti + 0.0f) << 32) | r);
+                atomicMin(&s_best[wid][own], key);
+            }
+        }
+    };
+
+    while (true) {
+        // ---- refill idle lanes from the queue (one atomicAdd per warp)
+        unsigned idle = __ballot_sync(FULL, !have);
+        if (!drained && (__popc(idle) >= kRefill || idle == FULL)) {
+            unsigned base = 0;
+            int leader = __ffs(idle) - 1;
+            if ((int)lane == leader) base = atomicAdd(head, (unsigned)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (!have) {
+                unsigned idx = base + __popc(idle & lt);
+                if (idx < count) {
+                    slot = w.queue[idx];
+                    float4 r0 = src[slot], r1 = src[n + slot];
+                    f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
+                    AabbHit binter = interAABB(o, d, g.bound);
+                    walkInit(f.w, PRIM, o, d, r1.w, g, binter);
+                    flatEnterMacro(f, g, s_macro, mshift, mn);
+                    have = true;
+                }
+            }
+            if (base + __popc(idle) >= count) drained = true;
+            idle = __ballot_sync(FULL, !have);
+        }
+        if (idle == FULL) break;
+        // ---- per-lane stepping through empty / finished cells
+        for (int k = 0; k < kStepBurst; k++) {
+            bool stepping = have && f.i >= f.end;
+            if (!__any_sync(FULL, stepping)) break;
+            if (stepping) {
+                if (flatLeave(f)) {
+                    have = false;
+                    const Hit& h = f.w.h;
+                    if (ANY) {   // A10/code.cl:1185-1192
+                        if (h.i != 0xFFFFFFFFu) {
+                            float4 s0 = w.sh[slot];
+                            w.sh[slot] = make_float4(s0.x, s0.y, s0.z, h.t);
+                            float4 s1 = w.sh[n + slot];
+                            w.sh[n + slot] = make_float4(s1.x, s1.y, s1.z, h.t);
+                        }
+                    } else if (h.i != 0xFFFFFFFFu) {   // A10/code.cl:921-934
+                        f3 p = getPoint(f.w.o, f.w.d, h.t);
+                        f3 nrm;
+                        int m;
+                        if (PRIM == PRIM_SPHERE) {
+                            float4 sp = __ldg(g.prim + h.i);
+                            nrm = normalize(p - mk3(sp.x, sp.y, sp.z));
+                            m = (int)__ldg(set.matid + h.i);
+                        } else {
+                            float4 n0 = __ldg(set.normals + 3 * h.i), n1 = __ldg(set.normals + 3 * h.i + 1), n2 = __ldg(set.normals + 3 * h.i + 2);
+                            nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
+                            m = set.matid ? (int)__ldg(set.matid + h.i) : (int)set.scalar_matid;
+                        }
+                        float4 r1 = w.ray[n + slot];
+                        w.ray[n + slot] = make_float4(r1.x, r1.y, r1.z, h.t);
+                        w.poi[slot] = make_float4(p.x, p.y, p.z, __int_as_float(m));
+                        w.poi[n + slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+                    }
+                } else {
+                    flatEnterMacro(f, g, s_macro, mshift, mn);
+                }
+            }
+        }
+        // ---- test the references of every pending non-empty cell, as one list of (owner, reference) pairs
+        const bool pending = have && f.i < f.end;
+        if (!__any_sync(FULL, pending)) continue;
+        const unsigned c = pending ? f.end - f.i : 0u;
+        unsigned incl = c;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            unsigned v = __shfl_up_sync(FULL, incl, dd);
+            if ((int)lane >= dd) incl += v;
+        }
+        const unsigned P = __shfl_sync(FULL, incl, 31);
+        s_off[wid][lane] = incl - c;
+        s_best[wid][lane] = NONE;
+        __syncwarp();
+        unsigned ncand = 0;
+        for (unsigned base = 0; base < P; base += 32) {
+            const unsigned p = base + lane;
+            const bool valid = p < P;
+            unsigned own = 0;   // last lane whose exclusive offset is <= p (offsets are non-decreasing)
+#pragma unroll
+            for (int st = 16; st > 0; st >>= 1)
+                if (s_off[wid][own + st] <= p) own += st;
+            const unsigned ref = __shfl_sync(FULL, f.i, own) + (p - s_off[wid][own]);
+            bool pass = valid;
+            float dv = 0.f;
+            if (PRIM == PRIM_TRIANGLE) {
+                const f3 d = mk3(__shfl_sync(FULL, f.w.d.x, own), __shfl_sync(FULL, f.w.d.y, own), __shfl_sync(FULL, f.w.d.z, own));
+                if (valid) {
+                    float4 q = __ldg(set.pre_ng + ref);
+                    dv = dot(mk3(q.x, q.y, q.z), d);
+                    pass = dv > 0;   // the reference's first rejection (div <= 0), on the precomputed face vector
+                }
+            }
+            const unsigned m = __ballot_sync(FULL, pass);
+            if (pass) {
+                unsigned pos = ncand + __popc(m & lt);
+                s_cref[wid][pos] = ref;
+                s_cown[wid][pos] = own;
+                s_cdiv[wid][pos] = dv;
+            }
+            ncand += __popc(m);
+            __syncwarp();
+            if (ncand >= 32) {
+                testCandidates(32);
+                // keep the (< 32) leftovers at the front of the buffer
+                unsigned tr = 0, to = 0;
+                float td = 0.f;
+                const bool mv = lane + 32 < ncand;
+                if (mv) { tr = s_cref[wid][lane + 32]; to = s_cown[wid][lane + 32]; td = s_cdiv[wid][lane + 32]; }
+                __syncwarp();
+                if (mv) { s_cref[wid][lane] = tr; s_cown[wid][lane] = to; s_cdiv[wid][lane] = td; }
+                ncand -= 32;
+                __syncwarp();
+            }
+        }
+        if (ncand) testCandidates(ncand);
+        __syncwarp();
+        if (pending) {
+            const unsigned long long key = s_best[wid][lane];
+            if (key != NONE) {   // recompute the winner's floats on the owner lane (same operations, same bits)
+                const unsigned r = (unsigned)key;
+                float ti = 0.f, be = 0.f, ga = 0.f;
+                if (PRIM == PRIM_TRIANGLE) {
+                    float4 q = __ldg(set.pre_ng + r);
+                    float dv = dot(mk3(q.x, q.y, q.z), f.w.d);
+                    float4 q0 = __ldg(set.pre_pe + 3 * r), q1 = __ldg(set.pre_pe + 3 * r + 1), q2 = __ldg(set.pre_pe + 3 * r + 2);
+                    interTriangleFast(f.w.o, f.w.d, f.mint, f.maxt, dv, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
+                } else {
+                    interSphere(f.w.o, f.w.d, f.w.a_dd, f.mint, f.maxt, __ldg(g.prim + r), ti);
+                }
+                f.w.h.t = ti;
+                f.w.h.i = r;
+                f.w.h.beta = be;
+                f.w.h.gamma = ga;
+            }
+            f.i = f.end;   // cell done; flatLeave ends the walk if it produced the hit
+        }
+        __syncwarp();
     }
 }
 
@@ -882,10 +1105,14 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
         } else {
             const SetDev& set = sc.sets[s.set];
             const int walk_blocks = ctx->prop.multiProcessorCount * kWalkMinBlocks;   // persistent: one resident wave
-            const bool coop = r->o.mode != 3;   // mode 3 = per-lane flattened walkers (kept for comparison)
+            const bool coop = r->o.mode != 3;   // mode 3 = per-lane flattened walkers, mode 4 = per-cell cooperative walkers (kept for comparison)
+            const bool pairs = r->o.mode != 3 && r->o.mode != 4;
             RT_TRY_W(rt_time_mark(r, (set.kind == PRIM_SPHERE ? 1 : 3) + (s.any ? 1 : 0)));
             if (set.kind == PRIM_SPHERE) {
-                if (coop) {
+                if (pairs) {
+                    if (s.any) k_walk_pairs<PRIM_SPHERE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
+                    else k_walk_pairs<PRIM_SPHERE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
+                } else if (coop) {
                     if (s.any) k_walk_coop<PRIM_SPHERE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
                     else k_walk_coop<PRIM_SPHERE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
                 } else {
@@ -893,7 +1120,10 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
                     else k_walk<PRIM_SPHERE, false><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
                 }
             } else {
-                if (coop && set.pre_ng) {
+                if (pairs && set.pre_ng) {
+                    if (s.any) k_walk_pairs<PRIM_TRIANGLE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
+                    else k_walk_pairs<PRIM_TRIANGLE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
+                } else if (coop && set.pre_ng) {
                     if (s.any) k_walk_coop<PRIM_TRIANGLE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
                     else k_walk_coop<PRIM_TRIANGLE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
                 } else {

@@ -197,8 +197,9 @@ typedef struct {
     float lens_rad;               /* scene.lens_diameter / 2 */
     unsigned slot_begin, slot_count;   /* multi-GPU: this context renders slots k in [slot_begin, slot_begin+slot_count)
                                           of every pixel; 0,0 = all rays_per_pixel slots */
-    unsigned mode;                /* 0 = fused wavefront path (default), 1 = reference kernel-by-kernel schedule */
-    unsigned tile_slots;          /* wavefront tile size in ray slots, 0 = auto */
+    unsigned mode;                /* 0 = wavefront path (default), 1 = reference kernel-by-kernel schedule, 2 = megakernel,
+                                     3 / 4 = earlier queue-walker designs (per-lane, per-cell cooperative), kept for A/B */
+    unsigned tile_slots;          /* wavefront tile size in ray slots, 0 = auto (a quarter of device memory) */
 } rt_render_opts;
 
 /* preRender: allocates ray/hit/accumulation state (A10/code.js:1078-1138, 1417-1442). */

@@ -179,10 +179,10 @@ def test_every_kernel_matches_oracle(rt, gpu_ctx, oracle_lib, scenes):
     assert pix[:, :3].max() > 30, "image is not trivially black"
 
 
-@pytest.mark.parametrize("mode", [1, 0, 2, 3])
+@pytest.mark.parametrize("mode", [1, 0, 2, 3, 4])
 def test_render_frame_matches_oracle(rt, oracle_lib, scenes, mode):
-    """rt_render_execute (mode 1 = reference schedule, mode 0 = wavefront stages + queue walkers,
-    mode 2 = megakernel) vs the
+    """rt_render_execute (mode 1 = reference schedule, mode 0 = wavefront stages + pair-list queue
+    walkers, mode 2 = megakernel, mode 3 / 4 = earlier walker designs kept for comparison) vs the
     oracle's executeRender: per-pixel float accumulation within 1e-3 (BASELINE.md gate 4; in
     practice bit-exact), seed buffer equal as integers, two progressive passes."""
     o_scene, p_scene = scenes
