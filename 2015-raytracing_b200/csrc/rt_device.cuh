@@ -506,29 +506,23 @@ RT_DEV void flatEnterMacro(FlatWalker& f, const GridView& g, const unsigned* s_m
     f.end = end;
 }
 
-// Leave the current cell (A10/code.cl:766-785).  Returns true when the walk is over.
+// Leave the current cell (A10/code.cl:766-785).  Returns true when the walk is over.  Written without the
+// reference's three-way branch (lanes of a warp step along different axes and would serialise it): the axis
+// is chosen with the same float equalities in the same x, y, z priority; t_next is advanced before the
+// `t >= tmax` test exactly as in the reference (the slab update of a finished walk is dead either way).
 RT_DEV bool flatLeave(FlatWalker& f) {
     Walker& w = f.w;
     if (w.h.i != 0xFFFFFFFFu) return true;
-    float t = f.maxt;
+    const float t = f.maxt;
     w.t = t;
-    if (t == w.ax.t_next) {
-        w.ax.t_next += w.ax.delta_t;
-        if (t >= w.tmax_b) return true;
-        w.ax.slab += w.ax.step;
-        if (w.ax.slab == w.ax.limit) return true;
-    } else if (t == w.ay.t_next) {
-        w.ay.t_next += w.ay.delta_t;
-        if (t >= w.tmax_b) return true;
-        w.ay.slab += w.ay.step;
-        if (w.ay.slab == w.ay.limit) return true;
-    } else {
-        w.az.t_next += w.az.delta_t;
-        if (t >= w.tmax_b) return true;
-        w.az.slab += w.az.step;
-        if (w.az.slab == w.az.limit) return true;
-    }
-    return false;
+    const bool bx = (t == w.ax.t_next);
+    const bool by = !bx && (t == w.ay.t_next);
+    const bool bz = !bx && !by;
+    if (bx) { w.ax.t_next += w.ax.delta_t; w.ax.slab += w.ax.step; }
+    if (by) { w.ay.t_next += w.ay.delta_t; w.ay.slab += w.ay.step; }
+    if (bz) { w.az.t_next += w.az.delta_t; w.az.slab += w.az.step; }
+    const bool out = (bx && w.ax.slab == w.ax.limit) || (by && w.ay.slab == w.ay.limit) || (bz && w.az.slab == w.az.limit);
+    return (t >= w.tmax_b) || out;
 }
 
 // Test reference f.i of the current cell (A10/code.cl:882-897) and advance the cursor.
@@ -589,29 +583,68 @@ RT_DEV Hit singleCellWalk(f3 o, f3 d, float maxt_in, const GridView& g, const fl
     const unsigned begin = __ldg(g.box), end = __ldg(g.box + 1);
     const float a_dd = (PRIM == PRIM_SPHERE) ? dot(d, d) : 0.f;
     if (STATS) st->cells++;
-    for (unsigned i = begin; i < end; i++) {
-        float ti, be = 0.f, ga = 0.f;
-        bool v;
-        if (PRIM == PRIM_SPHERE) {
-            v = interSphere(o, d, a_dd, mint, maxt, __ldg(g.prim + i), ti);
-        } else {
-            float4 q = __ldg(pre_ng + i);
-            float div = dot(mk3(q.x, q.y, q.z), d);
-            v = false;
-            if (div > 0) {
-                float4 q0 = __ldg(pre_pe + 3 * i), q1 = __ldg(pre_pe + 3 * i + 1), q2 = __ldg(pre_pe + 3 * i + 2);
-                v = interTriangleFast(o, d, mint, maxt, div, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
+    if (PRIM == PRIM_SPHERE) {
+        for (unsigned i = begin; i < end; i++) {
+            float ti;
+            bool v = interSphere(o, d, a_dd, mint, maxt, __ldg(g.prim + i), ti);
+            if (STATS) st->tests++;
+            if (v && ti < h.t) {
+                h.t = ti;
+                h.i = i;
+                h.cx = h.cy = h.cz = 0;
+                if (ANY) break;
             }
         }
-        if (STATS) st->tests++;
-        if (v && ti < h.t) {
-            h.t = ti;
-            h.i = i;
-            h.beta = be;
-            h.gamma = ga;
-            h.cx = h.cy = h.cz = 0;
-            if (ANY) break;
+    } else {
+    // Triangles, 32 references at a time, in three passes so that the lanes of a warp (which all loop over the
+    // SAME references but reject them at different points) do not serialise each other's rejections:
+    //   1. face-vector cull for every reference (uniform, cheap)            -> bit mask of front-facing ones
+    //   2. the two barycentric numerators for the survivors (each lane walks ITS OWN set bits) -> mask of
+    //      references with both numerators non-negative (interTriangleFast's sign rejections)
+    //   3. the division and the range tests for what is left, in ascending reference order, applying the
+    //      reference's `inter.v && inter.t < champ_t` update (and the any-hit break) exactly as the plain loop does.
+    // Rejections have no side effects, so the outcome (winner and floats) is that of the sequential loop.
+    for (unsigned base = begin; base < end; base += 32) {
+        const unsigned cnt = min(32u, end - base);
+        unsigned m1 = 0, minf = 0;
+        for (unsigned j = 0; j < cnt; j++) {
+            float4 q = __ldg(pre_ng + base + j);
+            float dv = dot(mk3(q.x, q.y, q.z), d);
+            if (dv > 0) m1 |= 1u << j;
+            if (dv == RT_INF) minf |= 1u << j;   // interTriangleFast does not apply the sign rejections then
         }
+        unsigned m2 = minf;
+        for (unsigned m = m1 & ~minf; m; m &= m - 1) {
+            const unsigned j = __ffs(m) - 1, r = base + j;
+            float4 q0 = __ldg(pre_pe + 3 * r), q1 = __ldg(pre_pe + 3 * r + 1), q2 = __ldg(pre_pe + 3 * r + 2);
+            f3 s = o - mk3(q0.x, q0.y, q0.z);
+            float nb = dot(cross(s, d), mk3(q2.x, q2.y, q2.z));
+            float ngm = dot(cross(s, mk3(q1.x, q1.y, q1.z)), d);
+            if (!(nb < 0.0f || ngm < 0.0f)) m2 |= 1u << j;
+        }
+        bool stop = false;
+        for (unsigned m = m2; m; m &= m - 1) {
+            const unsigned j = __ffs(m) - 1, r = base + j;
+            float4 q = __ldg(pre_ng + r);
+            float div = dot(mk3(q.x, q.y, q.z), d);
+            float4 q0 = __ldg(pre_pe + 3 * r), q1 = __ldg(pre_pe + 3 * r + 1), q2 = __ldg(pre_pe + 3 * r + 2);
+            float ti, be, ga;
+            if (interTriangleFast(o, d, mint, maxt, div, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti) && ti < h.t) {
+                h.t = ti;
+                h.i = r;
+                h.beta = be;
+                h.gamma = ga;
+                h.cx = h.cy = h.cz = 0;
+                if (ANY) {
+                    if (STATS) st->tests += j + 1;   // the reference's loop broke here
+                    stop = true;
+                    break;
+                }
+            }
+        }
+        if (stop) break;
+        if (STATS) st->tests += cnt;
+    }
     }
     return h;
 }

@@ -789,7 +789,8 @@ template <int PRIM, bool ANY>
 __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w,
                                                                                unsigned n, int qslot) {
     __shared__ unsigned s_macro[8192];   // 64^3 bits
-    __shared__ unsigned s_off[kWalkWarps][32];
+    __shared__ unsigned s_plist[kWalkWarps][32];   // pending lanes in lane order ...
+    __shared__ unsigned s_poff[kWalkWarps][32];    // ... and where their pairs start in the list
     __shared__ unsigned s_cref[kWalkWarps][kCandCap];
     __shared__ unsigned s_cown[kWalkWarps][kCandCap];
     __shared__ float s_cdiv[kWalkWarps][kCandCap];
@@ -912,18 +913,27 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
             if ((int)lane >= dd) incl += v;
         }
         const unsigned P = __shfl_sync(FULL, incl, 31);
-        s_off[wid][lane] = incl - c;
+        const unsigned off = incl - c;                       // start of this lane's pairs in the list
+        const unsigned pmask = __ballot_sync(FULL, pending);
+        if (pending) {
+            s_plist[wid][__popc(pmask & lt)] = lane;
+            s_poff[wid][__popc(pmask & lt)] = off;
+        }
         s_best[wid][lane] = NONE;
         __syncwarp();
         unsigned ncand = 0;
         for (unsigned base = 0; base < P; base += 32) {
             const unsigned p = base + lane;
             const bool valid = p < P;
-            unsigned own = 0;   // last lane whose exclusive offset is <= p (offsets are non-decreasing)
-#pragma unroll
-            for (int st = 16; st > 0; st >>= 1)
-                if (s_off[wid][own + st] <= p) own += st;
-            const unsigned ref = __shfl_sync(FULL, f.i, own) + (p - s_off[wid][own]);
+            // owner of pair p = the last pending lane whose list offset is <= p.  Rank it instead of searching:
+            // pending lanes that start before this batch are counted with one ballot, the ones that start inside
+            // it set a bit at their start position (offsets of pending lanes are distinct), and a popc of the
+            // bits up to this lane's position gives the rank into the ordered list of pending lanes.
+            const unsigned before = __popc(__ballot_sync(FULL, pending && off <= base));
+            const unsigned starts = __reduce_or_sync(FULL, (pending && off > base && off < base + 32) ? (1u << (off - base)) : 0u);
+            const unsigned rank = before + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));   // >= 1 for valid pairs
+            const unsigned own = s_plist[wid][(rank ? rank : 1u) - 1u];
+            const unsigned ref = __shfl_sync(FULL, f.i, own) + (p - s_poff[wid][(rank ? rank : 1u) - 1u]);
             bool pass = valid;
             float dv = 0.f;
             if (PRIM == PRIM_TRIANGLE) {
