@@ -191,8 +191,8 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
         per[k] = {"launches_per_step": n_l // args.steps, "launch_ms": round(ms_launch, 4), "algorithmic_bytes_per_launch": int(b_launch),
                   "achieved_gbs": round(b_launch / (ms_launch * 1e-3) / 1e9, 2), "share_of_step": round(v["ms"] / kern_ms, 4)}
     d = per[dom]
-    name = {"walk_triangle_closest": "k_walk_coop<triangle, closest hit>", "walk_triangle_any": "k_walk_coop<triangle, any hit>",
-            "walk_sphere_closest": "k_walk_coop<sphere, closest hit>", "walk_sphere_any": "k_walk_coop<sphere, any hit>"}[dom]
+    name = {"walk_triangle_closest": "k_walk_pairs<triangle, closest hit>", "walk_triangle_any": "k_walk_pairs<triangle, any hit>",
+            "walk_sphere_closest": "k_walk_pairs<sphere, closest hit>", "walk_sphere_any": "k_walk_pairs<sphere, any hit>"}[dom]
     return {"bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": round(d["achieved_gbs"] / peak, 4),
             "traffic": NCU_TRAFFIC.get(dom), "kernel": name, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if measured_peak else "fallback",
             "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "launch_ms": d["launch_ms"],

@@ -214,3 +214,76 @@ def test_render_frame_matches_oracle(rt, oracle_lib, scenes, mode):
         assert st.n_closest + st.n_any > 0
     finally:
         r.postRender()
+
+
+def test_full_size_frame_rows_match_oracle(rt, oracle_lib, tmp_path):
+    """BASELINE config 5 geometry at full size -- 1920x1080, the synthetic 1 000 000-triangle <mesh> at
+    nslabs 128 -- rendered whole on the GPU; the oracle renders a band of pixel rows of the same frame
+    (every kernel is per-slot independent, so a row tile is exact) and must agree bit for bit on the
+    accumulation image and on the seed buffer of those rows.  Also checks the two size-independent
+    invariances of the pipeline: the result does not depend on the wavefront tile size, nor on how
+    the slots of a pixel are split between renderers (the multi-GPU partition)."""
+    import synth
+    cols, rows, rpp = 1920, 1080, 4
+    mesh_json = synth.synth_mesh(1000, 500, seed=2015)
+    path = synth.write_scene(tmp_path, n_lights=2, with_sphere=True, with_mesh=True, mesh_nslabs=128)
+    o_scene = OH.loadScene(path, cols, rows, mesh_loader=lambda _f: OH.parseMeshJSON(mesh_json))
+    p_scene = rt.loadScene(path, cols, rows, mesh_loader=lambda _f: rt.parseMeshJSON(mesh_json))
+    total = cols * rows * rpp
+    seeds0 = OR.make_seeds(total, 2015)
+    r = rt.Renderer(p_scene, cols, rows, rpp)
+    r.preRender(seeds0)
+    try:
+        # the GPU grid build of the 1 M-triangle mesh against the oracle's cell lists
+        om, g = o_scene["meshes"][0], p_scene["meshes"][0].grid
+        d = rt.host.DeviceGrid(r.ctx, g, np.zeros(8, np.float32))
+        assert np.array_equal(d.box_size(), np.asarray(om.boxSizeData, np.uint32))
+        assert np.array_equal(d.prim().view(np.uint32), OH.to_f32(om.posData).view(np.uint32))
+        r.executeRender(readback=False)
+        acc = r.accum().reshape(rows, cols, 4)
+        seeds1 = r.seeds().reshape(rows, cols * rpp)
+        stats = r.stats()
+    finally:
+        r.postRender()
+    assert stats["closest_rays"] > 6 * 0.5 * cols * rows * rpp
+    prep = OR.prepare_a10(o_scene, 1)
+    cam = o_scene["camera"].toFloat32Array()
+    for row0, nrows in ((0, 2), (537, 6), (1078, 2)):
+        band = seeds0.reshape(rows, cols * rpp)[row0:row0 + nrows].reshape(-1)
+        st = OR.A10State(cols * nrows * rpp, band)
+        oracle_lib.a10_initAcu(st.acu, st.total)
+        OR.a10_execute_render(oracle_lib, st, prep, cam, cols, rows, rpp, o_scene["focal_length"], o_scene["lens_diameter"], row0=row0, nrows=nrows)
+        ref = np.zeros((cols * nrows, 4), np.float32)
+        for k in range(rpp):
+            ref += st.acu.reshape(cols * nrows, rpp, 4)[:, k]
+        got = acc[row0:row0 + nrows].reshape(-1, 4)
+        assert np.abs(got[:, :3] - ref[:, :3]).max() / rpp <= 1e-3
+        assert np.array_equal(seeds1[row0:row0 + nrows].reshape(-1), st.seeds), "RNG streams differ in rows %d.." % row0
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "expected bit-exact rows %d.." % row0
+    # tile-size invariance and slot-split invariance (bit-exact seeds; accumulation: same per-slot values, the
+    # per-pixel sum of a split render is the sum of the partial sums)
+    p2 = rt.loadScene(path, cols, rows, mesh_loader=lambda _f: rt.parseMeshJSON(mesh_json))
+    ra = rt.Renderer(p2, cols, rows, rpp, tile_slots=1 << 20)
+    ra.preRender(seeds0)
+    try:
+        ra.executeRender(readback=False)
+        assert np.array_equal(ra.accum().view(np.uint32).reshape(rows, cols, 4), acc.view(np.uint32))
+        assert np.array_equal(ra.seeds().reshape(rows, cols * rpp), seeds1)
+        ctx = ra.ctx
+        parts, accs = [], []
+        for rank in range(2):
+            b, c = rt.multi.slot_range(rank, 2, rpp)
+            p3 = rt.loadScene(path, cols, rows, mesh_loader=lambda _f: rt.parseMeshJSON(mesh_json))
+            rb = rt.Renderer(p3, cols, rows, rpp, slots=(b, c), ctx=ctx)
+            rb.preRender(seeds0)
+            try:
+                rb.executeRender(readback=False)
+                parts.append((b, c, rb.seeds()))
+                accs.append(rb.accum())
+            finally:
+                rb.postRender()
+        assert np.array_equal(rt.multi.merge_seeds(parts, cols * rows, rpp), seeds1.reshape(-1))
+        both = accs[0] + accs[1]
+        assert np.abs(both - acc.reshape(-1, 4)).max() <= 1e-5 * max(1.0, float(np.abs(acc).max()))
+    finally:
+        ra.postRender()
