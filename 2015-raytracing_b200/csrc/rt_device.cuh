@@ -525,6 +525,63 @@ RT_DEV bool flatLeave(FlatWalker& f) {
     return (t >= w.tmax_b) || out;
 }
 
+// Leave the current cell, or -- when `skip` says the cell lies in an EMPTY aligned 2x2x2 block of cells -- the
+// whole block, in one go.  Exact: it produces the state the reference's cell-by-cell loop (A10/code.cl:766-785)
+// has after the same steps.  Each axis' t_next sequence depends only on that axis (t_next += delta_t per step),
+// and the loop executes the pending steps of the three axes in lexicographic order of (t_next value, axis x<y<z):
+// `t = min(...)`, then `t == tx_next` first, `t == ty_next` second.  So: the block is left by the axis whose
+// boundary-crossing step (its 1st or 2nd step from here: r = 1 or 2) comes first in that order; every other axis
+// takes its first step iff that step precedes the crossing step in the same order (it then has r = 2 and stays
+// inside the block).  All cells passed on the way are empty, the `t >= tmax` test of a skipped step can only
+// fire when it also fires for the crossing step (its t is larger), and with an even n a skipped step never
+// reaches the grid limit.  With skip = false every r is 1 and this IS the reference step.
+// Callers pass skip = true only for rays whose t_next / delta_t are all finite (no zero direction component).
+RT_DEV bool flatAdvance(FlatWalker& f, bool skip) {
+    Walker& w = f.w;
+    if (w.h.i != 0xFFFFFFFFu) return true;
+    const bool two_x = skip && (((w.ax.slab & 1) != 0) == (w.ax.step < 0));   // two steps to the block face
+    const bool two_y = skip && (((w.ay.slab & 1) != 0) == (w.ay.step < 0));
+    const bool two_z = skip && (((w.az.slab & 1) != 0) == (w.az.step < 0));
+    const float Tx = two_x ? w.ax.t_next + w.ax.delta_t : w.ax.t_next;         // t of the crossing step
+    const float Ty = two_y ? w.ay.t_next + w.ay.delta_t : w.ay.t_next;
+    const float Tz = two_z ? w.az.t_next + w.az.delta_t : w.az.t_next;
+    const float t = cl_min(cl_min(Tx, Ty), Tz);
+    w.t = t;
+    const bool ex = (t == Tx);
+    const bool ey = !ex && (t == Ty);
+    const bool ez = !ex && !ey;
+    // first steps of the non-crossing axes that come before the crossing step (only possible when they have two)
+    const bool kx = !ex && two_x && (w.ax.t_next <= t);                         // x precedes y and z on ties
+    const bool ky = !ey && two_y && (ex ? (w.ay.t_next < t) : (w.ay.t_next <= t));
+    const bool kz = !ez && two_z && (w.az.t_next < t);
+    if (ex) { w.ax.t_next = Tx + w.ax.delta_t; w.ax.slab += two_x ? 2 * w.ax.step : w.ax.step; }
+    if (ey) { w.ay.t_next = Ty + w.ay.delta_t; w.ay.slab += two_y ? 2 * w.ay.step : w.ay.step; }
+    if (ez) { w.az.t_next = Tz + w.az.delta_t; w.az.slab += two_z ? 2 * w.az.step : w.az.step; }
+    if (kx) { w.ax.t_next += w.ax.delta_t; w.ax.slab += w.ax.step; }
+    if (ky) { w.ay.t_next += w.ay.delta_t; w.ay.slab += w.ay.step; }
+    if (kz) { w.az.t_next += w.az.delta_t; w.az.slab += w.az.step; }
+    const bool out = (ex && w.ax.slab == w.ax.limit) || (ey && w.ay.slab == w.ay.limit) || (ez && w.az.slab == w.az.limit);
+    return (t >= w.tmax_b) || out;
+}
+
+// Enter the cell the walker stands in; returns true when its coarse block is empty (nothing loaded, the
+// cell interval is not needed: flatAdvance works from t_next).  `coarse2` = the coarse bitmap has 2x2x2 blocks.
+RT_DEV bool flatEnterSkip(FlatWalker& f, const GridView& g, const unsigned* s_macro, unsigned shift, unsigned nm) {
+    Walker& w = f.w;
+    unsigned mc = ((unsigned)w.az.slab >> shift) * (nm * nm) + ((unsigned)w.ay.slab >> shift) * nm + ((unsigned)w.ax.slab >> shift);
+    f.i = 0;
+    f.end = 0;
+    if (!((s_macro[mc >> 5] >> (mc & 31)) & 1u)) return true;
+    f.mint = w.t;
+    f.maxt = cl_min(cl_min(w.ax.t_next, w.ay.t_next), w.az.t_next);
+    unsigned cell = (unsigned)w.az.slab * (g.n * g.n) + (unsigned)w.ay.slab * g.n + (unsigned)w.ax.slab;
+    if ((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u) {
+        f.i = __ldg(g.box + cell);
+        f.end = __ldg(g.box + cell + 1);
+    }
+    return false;
+}
+
 // Test reference f.i of the current cell (A10/code.cl:882-897) and advance the cursor.
 template <int PRIM, bool ANY>
 RT_DEV void flatTest(FlatWalker& f, const GridView& g) {

@@ -194,15 +194,18 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
     name = {"walk_triangle_closest": "k_walk_pairs<triangle, closest hit>", "walk_triangle_any": "k_walk_pairs<triangle, any hit>",
             "walk_sphere_closest": "k_walk_pairs<sphere, closest hit>", "walk_sphere_any": "k_walk_pairs<sphere, any hit>"}[dom]
     return {"bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": round(d["achieved_gbs"] / peak, 4),
-            "traffic": NCU_TRAFFIC.get(dom), "kernel": name, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if measured_peak else "fallback",
+            "traffic": (int(NCU_TRAFFIC[dom] * (args.cols * args.rows * args.spp / max(args.gpus, 1)) / NCU_TRAFFIC_SLOTS) if dom in NCU_TRAFFIC else None),
+            "kernel": name, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if measured_peak else "fallback",
             "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "launch_ms": d["launch_ms"],
             "share_of_step": d["share_of_step"], "kernels": per, "step": step,
             "work_per_set": alg["per_set"][:len(kinds)]}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch (4 Mi-slot tile) of the walker kernels, from the
-# committed `ncu --set full` capture (profiles/r1_walk_full_summary.md; mean over the captured launches)
-NCU_TRAFFIC = {"walk_triangle_any": 497020757, "walk_triangle_closest": 487735552}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the walker kernels from the committed `ncu --set full`
+# capture of this command at N = 1 (profiles/r1b_walk_full_summary.md: one tile = the whole frame, 530 841 600 slots
+# per launch; mean over the captured launches).  For N > 1 a launch covers 1/N of the slots and the figure is scaled.
+NCU_TRAFFIC = {"walk_triangle_any": 21283724688, "walk_triangle_closest": 21830812956}
+NCU_TRAFFIC_SLOTS = 1920 * 1080 * 256
 
 
 # ------------------------------------------------------------------------------ main
