@@ -334,6 +334,10 @@ RT_DEV void pushTask(bool want, unsigned id, unsigned* queue, unsigned* count) {
 #ifndef RT_STAGE_MINB
 #define RT_STAGE_MINB 4
 #endif
+// GEN / LR / SHADE / SHADOW / KIND mirror StageOp's gen, light_render, shade_light >= 0, shadow_light >= 0 and kind; they are
+// template parameters so that each of the few stage shapes a pass is made of gets its own register allocation (the
+// all-in-one kernel needed 80 registers or spilled ~400 B at 64).  The light indices and set ranges stay run-time values.
+template <int GEN, bool LR, bool SHADE, bool SHADOW, int KIND>
 __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_constant__ SceneDev sc, const __grid_constant__ PathArgs a,
                                                const __grid_constant__ WaveState w, const __grid_constant__ StageOp op) {
     unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -346,20 +350,20 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
         RayR ray, sr;
         bool poi_dirty = false, ray_dirty = false, sr_dirty = false, atte_dirty = false;
         // ---- load what this stage needs
-        if (op.gen != 1) {
+        if (GEN != 1) {
             float4 p0 = w.poi[id], p1 = w.poi[n + id];
             poi.p = mk3(p0.x, p0.y, p0.z); poi.matId = __float_as_int(p0.w);
             poi.n = mk3(p1.x, p1.y, p1.z);
             float4 at = w.atte[id];
             poi.atte = mk3(at.x, at.y, at.z);
         }
-        bool need_ray = (op.gen == 0) && (op.light_render || (op.kind == 0 && (op.set_hi > op.set_lo || op.push_set >= 0)));
+        bool need_ray = (GEN == 0) && (LR || (KIND == 0 && (op.set_hi > op.set_lo || op.push_set >= 0)));
         if (need_ray) {
             float4 r0 = w.ray[id], r1 = w.ray[n + id];
             ray.o = mk3(r0.x, r0.y, r0.z); ray.mint = r0.w;
             ray.d = mk3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
         }
-        bool need_sr = (op.shade_light >= 0) || (op.shadow_light < 0 && op.kind == 1 && (op.set_hi > op.set_lo || op.push_set >= 0));
+        bool need_sr = SHADE || (!SHADOW && KIND == 1 && (op.set_hi > op.set_lo || op.push_set >= 0));
         if (need_sr) {
             float4 s0 = w.sh[id], s1 = w.sh[n + id];
             sr.o = mk3(s0.x, s0.y, s0.z); sr.mint = s0.w;
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
         float4 acu;
         bool acu_loaded = false;
         // ---- sceneRender of the previous shadow ray (A10/code.cl:1323-1364)
-        if (op.shade_light >= 0 && poi.matId >= 0) {
+        if (SHADE && poi.matId >= 0) {
             const LightDev& L = sc.lights[op.shade_light];
             f3 shade = neeShade(poi.p, poi.n, sr.d, sr.maxt != sr.mint, L.scene);
             float4 color = __ldg(sc.materials + poi.matId);
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
             acu = make_float4(acu.x + contrib.x, acu.y + contrib.y, acu.z + contrib.z, acu.w + 1.0f);
         }
         // ---- new ray
-        if (op.gen == 1) {   // initTrace (A10/code.cl:458-543)
+        if (GEN == 1) {   // initTrace (A10/code.cl:458-543)
             Camera cam = floatToCamera(a.cam.v);
             AABB bound = toAABB(sc.bound);
             size_t pix = a.pixel_base + id / a.slots_pp;
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
             }
             ray_dirty = true;
             if (ray.mint != ray.maxt) n_closest++;
-        } else if (op.gen == 2) {   // bouncePaths (A10/code.cl:581-598)
+        } else if (GEN == 2) {   // bouncePaths (A10/code.cl:581-598)
             if (poi.matId >= 0) {
                 seed = a.seeds[id]; seed_loaded = true;
                 getHemisphereRay(poi.p, poi.n, seed, ray.o, ray.d);
@@ -431,7 +435,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
             ray_dirty = true;
         }
         // ---- lightRender for every light (A10/code.cl:600-629)
-        if (op.light_render) {
+        if (LR) {
             for (int l = 0; l < sc.n_lights; l++) {
                 if (ray.mint == ray.maxt) continue;
                 const LightArg& L = sc.lights[l].light;
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
             }
         }
         // ---- new shadow ray (A10/code.cl:631-673)
-        if (op.shadow_light >= 0) {
+        if (SHADOW) {
             if (poi.matId >= 0) {
                 if (!seed_loaded) { seed = a.seeds[id]; seed_loaded = true; }
                 sr = makeShadowRay(poi.p, poi.n, sc.lights[op.shadow_light].shadow, seed);
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
             sr_dirty = true;
         }
         // ---- small sets inline, in set order
-        if (op.kind == 0) {
+        if (KIND == 0) {
             for (int s = op.set_lo; s < op.set_hi; s++) {
                 float m0 = ray.maxt; int id0 = poi.matId;
                 closestSet<false, false>(sc.sets[s], ray, poi, nullptr);
@@ -507,7 +511,10 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
 // ended writes its result and becomes idle; when at least kRefill lanes of the warp are idle (or
 // none has work) the warp pops that many slot ids with ONE atomicAdd and the idle lanes set up
 // their DDA.  Every lane then advances its own ray by exactly one cell (walkCell).
-constexpr int kRefill = 8;
+#ifndef RT_REFILL
+#define RT_REFILL 8
+#endif
+constexpr int kRefill = RT_REFILL;
 
 template <int PRIM, bool ANY>
 __global__ void __launch_bounds__(256) k_walk(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w, unsigned n, int qslot) {
@@ -1118,6 +1125,36 @@ int ensureWaveBuffers(rt_render* r) {
     return rc;
 }
 
+// Picks the k_stage instantiation for a stage shape.  gen is 0/1/2, the rest are flags: 48 shapes exist on paper,
+// a pass uses about six of them; all are instantiated through one recursive dispatch.
+template <int GEN, bool LR, bool SHADE, bool SHADOW, int KIND>
+void launchStageT(rt_ctx* ctx, const SceneDev& sc, const PathArgs& a, const WaveState& w, const StageOp& op, unsigned n) {
+    k_stage<GEN, LR, SHADE, SHADOW, KIND><<<rt_blocks(n, 256), 256, 0, ctx->stream>>>(sc, a, w, op);
+}
+template <int GEN, bool LR, bool SHADE>
+void launchStage2(rt_ctx* ctx, const SceneDev& sc, const PathArgs& a, const WaveState& w, const StageOp& op, unsigned n) {
+    const bool shadow = op.shadow_light >= 0;
+    if (op.kind == 0) {
+        if (shadow) launchStageT<GEN, LR, SHADE, true, 0>(ctx, sc, a, w, op, n); else launchStageT<GEN, LR, SHADE, false, 0>(ctx, sc, a, w, op, n);
+    } else {
+        if (shadow) launchStageT<GEN, LR, SHADE, true, 1>(ctx, sc, a, w, op, n); else launchStageT<GEN, LR, SHADE, false, 1>(ctx, sc, a, w, op, n);
+    }
+}
+template <int GEN>
+void launchStage1(rt_ctx* ctx, const SceneDev& sc, const PathArgs& a, const WaveState& w, const StageOp& op, unsigned n) {
+    const bool shade = op.shade_light >= 0;
+    if (op.light_render) {
+        if (shade) launchStage2<GEN, true, true>(ctx, sc, a, w, op, n); else launchStage2<GEN, true, false>(ctx, sc, a, w, op, n);
+    } else {
+        if (shade) launchStage2<GEN, false, true>(ctx, sc, a, w, op, n); else launchStage2<GEN, false, false>(ctx, sc, a, w, op, n);
+    }
+}
+void launchStage(rt_ctx* ctx, const SceneDev& sc, const PathArgs& a, const WaveState& w, const StageOp& op, unsigned n) {
+    if (op.gen == 1) launchStage1<1>(ctx, sc, a, w, op, n);
+    else if (op.gen == 2) launchStage1<2>(ctx, sc, a, w, op, n);
+    else launchStage1<0>(ctx, sc, a, w, op, n);
+}
+
 int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
     rt_ctx* ctx = r->ctx;
     int rc = ensureWaveBuffers(r);
@@ -1136,7 +1173,7 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
     for (const Stage& s : stages) {
         if (!s.is_walk) {
             RT_TRY_W(rt_time_mark(r, 0));
-            k_stage<<<rt_blocks(n, 256), 256, 0, ctx->stream>>>(sc, a, w, s.op);
+            launchStage(ctx, sc, a, w, s.op, n);
             RT_LAUNCH_CHECK(ctx, "wave_stage");
         } else {
             const SetDev& set = sc.sets[s.set];
