@@ -259,7 +259,7 @@ int rt_scene_add_set(rt_scene* s, const rt_grid* grid, const float bound[8], int
     memcpy(st.bound, bound, sizeof st.bound);
     st.is_mesh = is_mesh;
     st.mesh_matid = mesh_matid;
-    if (grid->n_slabs > 2 && grid->n_refs > 64 && grid->occupancy) {   // "heavy" set: coarse occupancy for the queue walkers
+    if (grid->n_slabs > 1 && grid->occupancy) {   // multi-cell ("heavy") set: coarse occupancy for the queue walkers
         rt_ctx* ctx = s->ctx;
         unsigned sh = 0;
         while (((grid->n_slabs + (1u << sh) - 1) >> sh) > 64) sh++;

@@ -126,6 +126,39 @@ RT_DEV void flushProfile(unsigned* prof, unsigned long long* table, int set, int
     }
 }
 
+// The same two functions for the per-slot stage kernels, where every inline set is a ONE-cell grid (multi-cell
+// sets are "heavy" and go to the queue walkers): only singleCellWalk is compiled in.
+RT_DEV void closestSet1(const SetDev& s, RayR& ray, PoiR& poi) {
+    if (ray.mint == ray.maxt) return;
+    AabbHit binter = interAABB(ray.o, ray.d, s.g.bound);
+    if (!binter.v) return;
+    Hit h;
+    if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, false, false>(ray.o, ray.d, ray.maxt, s.g, nullptr, nullptr, binter, nullptr);
+    else h = singleCellWalk<PRIM_TRIANGLE, false, false>(ray.o, ray.d, ray.maxt, s.g, s.pre_ng, s.pre_pe, binter, nullptr);
+    if (h.i == 0xFFFFFFFFu) return;
+    ray.maxt = h.t;
+    poi.p = getPoint(ray.o, ray.d, h.t);
+    if (s.kind == PRIM_SPHERE) {
+        float4 sp = __ldg(s.g.prim + h.i);
+        poi.n = normalize(poi.p - mk3(sp.x, sp.y, sp.z));
+        poi.matId = (int)__ldg(s.matid + h.i);
+    } else {
+        float4 n0 = __ldg(s.normals + 3 * h.i), n1 = __ldg(s.normals + 3 * h.i + 1), n2 = __ldg(s.normals + 3 * h.i + 2);
+        poi.n = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
+        poi.matId = s.matid ? (int)__ldg(s.matid + h.i) : (int)s.scalar_matid;
+    }
+}
+RT_DEV void anySet1(const SetDev& s, RayR& sr) {
+    if (sr.mint == sr.maxt) return;
+    AabbHit binter = interAABB(sr.o, sr.d, s.g.bound);
+    if (!binter.v) return;
+    Hit h;
+    if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, true, false>(sr.o, sr.d, sr.maxt, s.g, nullptr, nullptr, binter, nullptr);
+    else h = singleCellWalk<PRIM_TRIANGLE, true, false>(sr.o, sr.d, sr.maxt, s.g, s.pre_ng, s.pre_pe, binter, nullptr);
+    if (h.i != 0xFFFFFFFFu) { sr.maxt = h.t; sr.mint = h.t; }
+    else sr.maxt = h.t;
+}
+
 template <bool STATS>
 RT_DEV void closestAllSets(const SceneDev& sc, RayR& ray, PoiR& poi, unsigned* prof, unsigned long long* table) {
     for (int s = 0; s < sc.n_sets; s++) {
@@ -266,7 +299,7 @@ int buildSceneDev(rt_render* r, SceneDev& sc) {
         d.matid = in.is_mesh ? nullptr : (const unsigned*)in.grid.matid;
         d.scalar_matid = in.mesh_matid;
         d.kind = in.grid.kind == 0 ? PRIM_SPHERE : PRIM_TRIANGLE;
-        d.use_occ = (in.grid.occupancy != nullptr && in.grid.n_slabs > 2) ? 1 : 0;
+        d.use_occ = (in.grid.occupancy != nullptr && in.grid.n_slabs > 1) ? 1 : 0;
         d.pre_ng = in.pre_ng;
         d.pre_pe = in.pre_pe;
         d.macro_occ = in.macro_occ;
@@ -467,14 +500,14 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
         if (KIND == 0) {
             for (int s = op.set_lo; s < op.set_hi; s++) {
                 float m0 = ray.maxt; int id0 = poi.matId;
-                closestSet<false, false>(sc.sets[s], ray, poi, nullptr);
+                closestSet1(sc.sets[s], ray, poi);
                 if (ray.maxt != m0 || poi.matId != id0) { ray_dirty = true; poi_dirty = true; }
             }
             if (op.push_set >= 0 && ray.mint != ray.maxt) want_push = interAABB(ray.o, ray.d, sc.sets[op.push_set].g.bound).v;
         } else {
             for (int s = op.set_lo; s < op.set_hi; s++) {
                 float m0 = sr.mint, x0 = sr.maxt;
-                anySet<false, false>(sc.sets[s], sr, nullptr);
+                anySet1(sc.sets[s], sr);
                 if (sr.mint != m0 || sr.maxt != x0) sr_dirty = true;
             }
             if (op.push_set >= 0 && sr.mint != sr.maxt) want_push = interAABB(sr.o, sr.d, sc.sets[op.push_set].g.bound).v;
@@ -1028,7 +1061,8 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
 // Builds the stage list for a scene (host) and runs one tile through it.
 struct Stage { bool is_walk; StageOp op; int set; bool any; int qslot; };
 
-bool isHeavy(const SceneSet& s) { return s.grid.n_slabs > 2 && s.grid.n_refs > 64 && s.grid.occupancy != nullptr; }
+// every multi-cell grid is walked by the queue walkers; 1-cell grids (all XML sets of A10) are intersected inline
+bool isHeavy(const SceneSet& s) { return s.grid.n_slabs > 1 && s.grid.occupancy != nullptr && s.macro_occ != nullptr; }
 
 // Appends the stages that trace the current ray kind against all sets, in set order.  `first` is
 // a per-slot op already holding the work that precedes the trace (shade / gen / shadow gen).

@@ -177,7 +177,7 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
         kinds.append(("triangle", m.grid))
     byts = {"walk_sphere_closest": 0, "walk_sphere_any": 0, "walk_triangle_closest": 0, "walk_triangle_any": 0}
     for row, (kind, g) in zip(alg["per_set"], kinds):
-        if not (g.n_slabs > 2 and g.n_refs > 64):
+        if not g.n_slabs > 1:   # 1-cell sets are intersected inline by the stage kernels
             continue
         # the walker sees only rays that hit the set's AABB: take the ray loads of the others out
         byts["walk_%s_closest" % kind] += row["closest_bytes"] - 48 * (row["closest_queries"] - row["closest_walks"])

@@ -216,6 +216,31 @@ def test_render_frame_matches_oracle(rt, oracle_lib, scenes, mode):
         r.postRender()
 
 
+@pytest.mark.parametrize("mode", [0, 1, 4])
+def test_render_frame_multi_cell_xml_sets(rt, oracle_lib, scenes, mode):
+    """Global n_slabs = 3 (the reference's commented-out UI input, A10/index.html:28): the XML sphere and triangle
+    sets become multi-cell grids too and are served by the queue walkers (sphere and triangle instantiations)."""
+    o_scene, p_scene = scenes
+    total = COLS * ROWS * RPP
+    seeds0 = OR.make_seeds(total, 23)
+    prep = OR.prepare_a10(o_scene, 3)
+    st = OR.A10State(total, seeds0)
+    oracle_lib.a10_initAcu(st.acu, total)
+    cam = o_scene["camera"].toFloat32Array()
+    OR.a10_execute_render(oracle_lib, st, prep, cam, COLS, ROWS, RPP, o_scene["focal_length"], o_scene["lens_diameter"])
+    r = rt.Renderer(p_scene, COLS, ROWS, RPP, n_slabs=3, mode=mode)
+    r.preRender(seeds0)
+    try:
+        r.executeRender()
+        ref = np.zeros((COLS * ROWS, 4), np.float32)
+        for k in range(RPP):
+            ref += st.acu.reshape(COLS * ROWS, RPP, 4)[:, k]
+        assert np.array_equal(r.seeds(), st.seeds)
+        assert np.array_equal(r.accum().view(np.uint32), ref.view(np.uint32))
+    finally:
+        r.postRender()
+
+
 def test_full_size_frame_rows_match_oracle(rt, oracle_lib, tmp_path):
     """BASELINE config 5 geometry at full size -- 1920x1080, the synthetic 1 000 000-triangle <mesh> at
     nslabs 128 -- rendered whole on the GPU; the oracle renders a band of pixel rows of the same frame
