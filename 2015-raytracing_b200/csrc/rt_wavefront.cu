@@ -365,7 +365,7 @@ RT_DEV void pushTask(bool want, unsigned id, unsigned* queue, unsigned* count) {
 }
 
 #ifndef RT_STAGE_MINB
-#define RT_STAGE_MINB 4
+#define RT_STAGE_MINB 5
 #endif
 // GEN / LR / SHADE / SHADOW / KIND mirror StageOp's gen, light_render, shade_light >= 0, shadow_light >= 0 and kind; they are
 // template parameters so that each of the few stage shapes a pass is made of gets its own register allocation (the
@@ -856,6 +856,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
     f.i = f.end = 0;
     unsigned slot = 0;
     bool have = false;
+    bool fin = false;       // walk ended with a hit that still has to be written back
     bool drained = false;
 #if RT_SKIP2
     // exact skipping of empty 2x2x2 blocks (flatAdvance): needs 2-cell coarse blocks, an even n and a ray without
@@ -892,9 +893,42 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
         }
     };
 
+    // Write the result of a finished walk (A10/code.cl:921-934 closest hit, :1185-1192 any hit).  Deferred to the refill
+    // step so that the lanes that finished since the last refill do it together instead of one at a time inside
+    // the stepping loop.
+    auto writeBack = [&]() {
+        const Hit& h = f.w.h;
+        if (ANY) {
+            float4 s0 = w.sh[slot];
+            w.sh[slot] = make_float4(s0.x, s0.y, s0.z, h.t);
+            float4 s1 = w.sh[n + slot];
+            w.sh[n + slot] = make_float4(s1.x, s1.y, s1.z, h.t);
+        } else {
+            f3 p = getPoint(f.w.o, f.w.d, h.t);
+            f3 nrm;
+            int m;
+            if (PRIM == PRIM_SPHERE) {
+                float4 sp = __ldg(g.prim + h.i);
+                nrm = normalize(p - mk3(sp.x, sp.y, sp.z));
+                m = (int)__ldg(set.matid + h.i);
+            } else {
+                float4 n0 = __ldg(set.normals + 3 * h.i), n1 = __ldg(set.normals + 3 * h.i + 1), n2 = __ldg(set.normals + 3 * h.i + 2);
+                nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
+                m = set.matid ? (int)__ldg(set.matid + h.i) : (int)set.scalar_matid;
+            }
+            float4 r1 = w.ray[n + slot];
+            w.ray[n + slot] = make_float4(r1.x, r1.y, r1.z, h.t);
+            w.poi[slot] = make_float4(p.x, p.y, p.z, __int_as_float(m));
+            w.poi[n + slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+        }
+    };
+
     while (true) {
         // ---- refill idle lanes from the queue (one atomicAdd per warp)
         unsigned idle = __ballot_sync(FULL, !have);
+        if (__popc(idle) >= kRefill || idle == FULL) {
+            if (fin) { writeBack(); fin = false; }
+        }
         if (!drained && (__popc(idle) >= kRefill || idle == FULL)) {
             unsigned base = 0;
             int leader = __ffs(idle) - 1;
@@ -933,32 +967,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
                 if (flatLeave(f)) {
 #endif
                     have = false;
-                    const Hit& h = f.w.h;
-                    if (ANY) {   // A10/code.cl:1185-1192
-                        if (h.i != 0xFFFFFFFFu) {
-                            float4 s0 = w.sh[slot];
-                            w.sh[slot] = make_float4(s0.x, s0.y, s0.z, h.t);
-                            float4 s1 = w.sh[n + slot];
-                            w.sh[n + slot] = make_float4(s1.x, s1.y, s1.z, h.t);
-                        }
-                    } else if (h.i != 0xFFFFFFFFu) {   // A10/code.cl:921-934
-                        f3 p = getPoint(f.w.o, f.w.d, h.t);
-                        f3 nrm;
-                        int m;
-                        if (PRIM == PRIM_SPHERE) {
-                            float4 sp = __ldg(g.prim + h.i);
-                            nrm = normalize(p - mk3(sp.x, sp.y, sp.z));
-                            m = (int)__ldg(set.matid + h.i);
-                        } else {
-                            float4 n0 = __ldg(set.normals + 3 * h.i), n1 = __ldg(set.normals + 3 * h.i + 1), n2 = __ldg(set.normals + 3 * h.i + 2);
-                            nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
-                            m = set.matid ? (int)__ldg(set.matid + h.i) : (int)set.scalar_matid;
-                        }
-                        float4 r1 = w.ray[n + slot];
-                        w.ray[n + slot] = make_float4(r1.x, r1.y, r1.z, h.t);
-                        w.poi[slot] = make_float4(p.x, p.y, p.z, __int_as_float(m));
-                        w.poi[n + slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
-                    }
+                    fin = f.w.h.i != 0xFFFFFFFFu;   // result written back in a batch, see the refill step
                 } else {
 #if RT_SKIP2
                     skip = flatEnterSkip(f, g, s_macro, mshift, mn) && finite;
