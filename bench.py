@@ -339,7 +339,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         roofline = roofline_of(r, scene, tclass, kern_ms, args, peak, bool(peaks))
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only
             cpu = cpu_baseline(args)
         out = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
@@ -382,6 +382,7 @@ def cpu_baseline(args):
     """Reference kernels on the host cores, on a bounded row sample of the same workload."""
     from oracle import refcl as OR
     olib = OR.load_best()
+    olib.set_num_threads(os.cpu_count() or 1)
     scene, prep = oracle_scene(args, tempfile.mkdtemp(prefix="rt_bench_cpu_"))
     cam = scene["camera"].toFloat32Array()
     rows = args.cpu_rows or cpu_rows_default(args, 15.0)
@@ -401,6 +402,7 @@ def main_reference(args, rank):
         return
     from oracle import refcl as OR
     olib = OR.load_best()
+    olib.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; this arm uses every host core
     scene, prep = oracle_scene(args, tempfile.mkdtemp(prefix="rt_bench_ref_"))
     cam = scene["camera"].toFloat32Array()
     rows = args.cpu_rows or cpu_rows_default(args, 8.0)

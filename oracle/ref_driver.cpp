@@ -92,6 +92,8 @@ extern "C" int ref_is_instrumented() {
 #endif
 }
 extern "C" int ref_num_threads() { return omp_get_max_threads(); }
+// launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline wants all host cores
+extern "C" void ref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 #define STAT_BEGIN() \
     ref_tl_cells = 0; ref_tl_tests = 0; ref_tl_hit = 0xFFFFFFFFu;

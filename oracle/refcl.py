@@ -105,6 +105,7 @@ class KernelLib:
             setattr(self, name, fn)
         self.num_threads = getattr(self._dll, prefix + "num_threads")
         self.num_threads.restype = _I
+        self.set_num_threads = getattr(self._dll, prefix + "set_num_threads", lambda n: None)
         self._set_stats = getattr(self._dll, prefix + "set_stats", None)
         if self._set_stats is not None:
             self._set_stats.argtypes = [_P, _P, _P]
