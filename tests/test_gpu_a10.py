@@ -312,3 +312,72 @@ def test_full_size_frame_rows_match_oracle(rt, oracle_lib, tmp_path):
         assert np.abs(both - acc.reshape(-1, 4)).max() <= 1e-5 * max(1.0, float(np.abs(acc).max()))
     finally:
         ra.postRender()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rays_per_pixel_one_serial_outcome(rt, oracle_lib, scenes, mode):
+    """rays_per_pixel == 1: the reference draws the lens sample from seeds[get_global_id(0)] = seeds[col] in a 2-D
+    launch, so all rows of a column race on one seed (quirk Q7).  The only defined outcome is the serial row-major
+    one; we implement it (column `col` hands draws 2*row, 2*row+1 of its stream to row `row`) and the oracle runs
+    the same kernel text single-threaded in that order."""
+    o_scene, p_scene = scenes
+    total = COLS * ROWS
+    seeds0 = OR.make_seeds(total, 31)
+    prep = OR.prepare_a10(o_scene, 1)
+    st = OR.A10State(total, seeds0)
+    oracle_lib.a10_initAcu(st.acu, total)
+    cam = o_scene["camera"].toFloat32Array()
+    r = rt.Renderer(p_scene, COLS, ROWS, 1, mode=mode)
+    r.preRender(seeds0)
+    try:
+        for _ in range(2):
+            pix_o = OR.a10_execute_render(oracle_lib, st, prep, cam, COLS, ROWS, 1, o_scene["focal_length"], o_scene["lens_diameter"], serial_init=True)
+            pix = r.executeRender()
+            assert np.array_equal(r.seeds(), st.seeds)
+            assert np.array_equal(r.accum().view(np.uint32), st.acu.view(np.uint32))
+            assert np.array_equal(pix.reshape(-1, 4), pix_o.reshape(-1, 4))
+    finally:
+        r.postRender()
+
+
+def test_error_paths_and_empty_launches(rt, gpu_ctx, scenes):
+    """Argument checking of the C ABI on a live context: bad arguments give RT_ERR_INVALID / RT_ERR_STATE with a
+    message, zero-sized launches are no-ops, a render refuses to run before its seeds are set."""
+    ctx, dll = gpu_ctx, rt.lib.dll
+    d = ctx.alloc(64)
+    assert dll.rt_a10_initAcu(ctx.h, d, 0) == 0
+    assert dll.rt_a10_bouncePaths(ctx.h, d, d, d, 0) == 0
+    assert dll.rt_a10_copyToPixel(ctx.h, d, d, 1.0, 0, 4) == 0
+    assert dll.rt_a10_initAcu(ctx.h, None, 4) == -1
+    assert dll.rt_a10_sphereTrace(ctx.h, 4, d, d, d, d, d, None, 1) == -1
+    assert dll.rt_a10_sphereTrace(ctx.h, 4, d, d, d, d, d, np.zeros(8, np.float32).ctypes.data, 0) == -1
+    assert dll.rt_buffer_write(ctx.h, d, 0, 16, None) == -1
+    _, p_scene = scenes
+    with pytest.raises(rt.lib.RtError, match="perfect square"):
+        r = rt.Renderer(p_scene, COLS, ROWS, 3, ctx=ctx)
+        r.preRender(None)
+    r = rt.Renderer(p_scene, 8, 8, 4, ctx=ctx)   # canvas differs from the scene camera's cols/rows
+    r.preRender(np.arange(1, 8 * 8 * 4 + 1, dtype=np.int32))
+    try:
+        with pytest.raises(rt.lib.RtError, match="camera cols/rows"):
+            r.executeRender()
+    finally:
+        r.postRender()
+    r = rt.Renderer(p_scene, COLS, ROWS, 4, ctx=ctx)
+    r.preRender(None)
+    try:
+        with pytest.raises(rt.lib.RtError, match="seeds not set"):
+            r.executeRender()
+        with pytest.raises(rt.lib.RtError, match="count must be"):
+            r.setSeeds(np.ones(5, np.int32))
+        r.setSeeds(np.arange(1, COLS * ROWS * 4 + 1, dtype=np.int32))
+        img = r.executeRender()
+        assert img.shape == (ROWS, COLS, 4) and img[..., 3].min() == 255
+    finally:
+        r.postRender()
+    with pytest.raises(rt.lib.RtError, match="slot range"):
+        r2 = rt.Renderer(p_scene, COLS, ROWS, 4, slots=(3, 2), ctx=ctx)
+        try:
+            r2.preRender(None)
+        finally:
+            r2.postRender()
