@@ -14,8 +14,8 @@ from . import lib  # noqa: F401  (fails loudly when librt2015.so is missing)
 from . import assignments, multi  # noqa: F401
 from .host import (  # noqa: F401
     Bounds, Camera, Light, Mesh, Renderer, Vec3, bounds2AABB, loadScene, parseMeshJSON, parsePDB,
-    splitMaterialData, splitMeshData, splitMolData, splitSphereData, splitTriangleData,
+    splitMaterialData, splitMeshData, splitMolData, splitSphereData, splitTriangleData, write_png,
 )
 
 __all__ = ["lib", "multi", "assignments", "Bounds", "Camera", "Light", "Mesh", "Renderer", "Vec3", "bounds2AABB", "loadScene", "parseMeshJSON",
-           "parsePDB", "splitMaterialData", "splitMeshData", "splitMolData", "splitSphereData", "splitTriangleData"]
+           "parsePDB", "splitMaterialData", "splitMeshData", "splitMolData", "splitSphereData", "splitTriangleData", "write_png"]

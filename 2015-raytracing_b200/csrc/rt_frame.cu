@@ -512,6 +512,25 @@ int rt_render_read_seeds(rt_render* r, int* host_seeds, size_t count) {
     return rt_buffer_read(r->ctx, r->seeds, 0, sizeof(int) * count, host_seeds);
 }
 
+int rt_render_export_state(rt_render* r, float* host_acu, int* host_seeds, unsigned* passes) {
+    if (!r) return RT_ERR_INVALID;
+    if (host_acu) RT_TRY(rt_buffer_read(r->ctx, r->acu, 0, sizeof(float4) * r->local_slots, host_acu));
+    if (host_seeds) RT_TRY(rt_buffer_read(r->ctx, r->seeds, 0, sizeof(int) * r->local_slots, host_seeds));
+    if (passes) *passes = r->passes;
+    return RT_OK;
+}
+
+int rt_render_import_state(rt_render* r, const float* host_acu, const int* host_seeds, unsigned passes) {
+    if (!r || passes == 0) return RT_ERR_INVALID;
+    if (host_acu) RT_TRY(rt_buffer_write(r->ctx, r->acu, 0, sizeof(float4) * r->local_slots, host_acu));
+    if (host_seeds) {
+        RT_TRY(rt_buffer_write(r->ctx, r->seeds, 0, sizeof(int) * r->local_slots, host_seeds));
+        r->have_seeds = true;
+    }
+    r->passes = passes;
+    return RT_OK;
+}
+
 int rt_accum_to_pixel(rt_ctx* ctx, void* pixel, const void* accum_float4, float m, unsigned pixels) {
     RT_CHECK_CTX(ctx);
     if (!pixel || !accum_float4) return RT_ERR_INVALID;

@@ -547,6 +547,24 @@ def loadScene(sceneName, width, height, mesh_loader=None, assignment=10):
             "triangleBounds": triangleBounds, "meshes": meshes}
 
 
+def write_png(path, rgba):
+    """sendImagetoHTML's canvas.putImageData (A10/code.js:1530-1537) for a headless host: the RGBA image a pass
+    returns as an 8-bit PNG (stdlib only)."""
+    import struct
+    import zlib
+    a = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = a.shape[0], a.shape[1]
+    raw = b"".join(b"\x00" + a[y].tobytes() for y in range(h))
+
+    def chunk(tag, data):
+        c = struct.pack(">I", len(data)) + tag + data
+        return c + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 6))
+                + chunk(b"IEND", b""))
+
+
 # ------------------------------------------------------------------------------ frame driver
 class Renderer:
     """preRender / executeRender / postRender of A10/code.js:1784-1859 on one GPU.
@@ -692,6 +710,22 @@ class Renderer:
                             "cells": int(row[2] + row[10]), "tests": int(row[3] + row[4] + row[11] + row[12])})
         return {"bytes_per_pass": int(c + a + stream), "traversal_bytes": int(c + a), "streaming_bytes": int(stream),
                 "profile": [int(v) for v in tot], "per_set": per_set}
+
+    # -- checkpoint / resume of the progressive state (acu, seeds, passes); the reference keeps it only on the device --
+    def export_state(self):
+        n = self.width * self.height * self.slots[1]
+        acu, seeds, passes = np.empty((n, 4), np.float32), np.empty(n, np.int32), L.U()
+        self.ctx.check(L.dll.rt_render_export_state(self.h_render, acu.ctypes.data, seeds.ctypes.data, C.byref(passes)))
+        return {"acu": acu, "seeds": seeds, "passes": int(passes.value)}
+
+    def import_state(self, state):
+        acu = np.ascontiguousarray(state["acu"], dtype=np.float32)
+        seeds = np.ascontiguousarray(state["seeds"], dtype=np.int32)
+        n = self.width * self.height * self.slots[1]
+        if acu.size != 4 * n or seeds.size != n:
+            raise ValueError("import_state: state belongs to a render of another size")
+        self.ctx.check(L.dll.rt_render_import_state(self.h_render, acu.ctypes.data, seeds.ctypes.data, int(state["passes"])))
+        self.passes = int(state["passes"])
 
     # -- postRender: A10/code.js:1856-1859 --
     def postRender(self):

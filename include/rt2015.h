@@ -220,6 +220,13 @@ int rt_render_read_seeds(rt_render*, int* host_seeds, size_t count);            
 /* Same as rt_render_set_seeds for a caller that already holds only THIS context's slots, laid out
  * [pixel][k_local] (count = cols*rows*slot_count host ints). */
 int rt_render_write_local_seeds(rt_render*, const int* host_seeds, size_t count);
+/* Progressive state of a render = what lives only on the device between passes in the reference: the per-slot
+ * accumulators, the per-slot seeds and the pass counter (A10/code.js:416, 1078-1099, 1140-1154, 1853).  Export after
+ * any pass, import into a render created with the same scene/options to resume bit-exactly where it stopped
+ * (checkpoint / resume; the reference loses this state on stopRender).  acu: cols*rows*slot_count float4,
+ * seeds: cols*rows*slot_count ints, both [pixel][k_local]; either pointer may be NULL to skip that part. */
+int rt_render_export_state(rt_render*, float* host_acu_float4, int* host_seeds, unsigned* passes);
+int rt_render_import_state(rt_render*, const float* host_acu_float4, const int* host_seeds, unsigned passes);
 /* copyToPixel on an accumulation image (after a multi-GPU reduce): m = 1/(rays_per_pixel*passes). */
 int rt_accum_to_pixel(rt_ctx*, void* pixel, const void* accum_float4, float m, unsigned pixels);
 /* Counters of the last execute: valid closest-hit and any-hit queries ("rays"),

@@ -30,6 +30,15 @@ def oracle_lib():
 
 
 @pytest.fixture(scope="session")
+def ref_lib(oracle_lib):
+    """The reference's own kernel text (oracle/_ref) -- needed for the assignments the plain-C restatement does not
+    cover (A01-A09); skipped where only the restatement is available."""
+    if oracle_lib.kind != "reference":
+        pytest.skip("oracle/_ref (the reference's own kernels) is not built here")
+    return oracle_lib
+
+
+@pytest.fixture(scope="session")
 def gpu_ctx(rt):
     ctx = rt.lib.Context(0)
     yield ctx

@@ -381,3 +381,44 @@ def test_error_paths_and_empty_launches(rt, gpu_ctx, scenes):
             r2.preRender(None)
         finally:
             r2.postRender()
+
+
+def test_checkpoint_resume_is_bit_exact(rt, scenes, tmp_path):
+    """Progressive display path: 3 passes in one go == 1 pass, export (acu, seeds, passes), import into a fresh
+    render, 2 more passes -- accumulation, seeds and the displayed image identical; the image goes out as a PNG."""
+    _, p_scene = scenes
+    total = COLS * ROWS * RPP
+    seeds0 = OR.make_seeds(total, 41)
+    a = rt.Renderer(p_scene, COLS, ROWS, RPP)
+    a.preRender(seeds0)
+    try:
+        for _ in range(3):
+            img_a = a.executeRender()
+        acc_a, seeds_a = a.accum(), a.seeds()
+        ctx = a.ctx
+        b = rt.Renderer(p_scene, COLS, ROWS, RPP, ctx=ctx)
+        b.preRender(seeds0)
+        try:
+            b.executeRender()
+            state = b.export_state()
+            assert state["passes"] == 2
+        finally:
+            b.postRender()
+        c = rt.Renderer(p_scene, COLS, ROWS, RPP, ctx=ctx)
+        c.preRender(None)
+        try:
+            c.import_state(state)
+            c.executeRender()
+            img_c = c.executeRender()
+            assert np.array_equal(c.seeds(), seeds_a)
+            assert np.array_equal(c.accum().view(np.uint32), acc_a.view(np.uint32))
+            assert np.array_equal(img_c, img_a)
+        finally:
+            c.postRender()
+    finally:
+        a.postRender()
+    png = tmp_path / "frame.png"
+    rt.write_png(str(png), img_a)
+    from PIL import Image
+    back = np.asarray(Image.open(str(png)).convert("RGBA"))
+    assert np.array_equal(back, img_a)

@@ -44,15 +44,15 @@ def test_a10_scene(oracle_lib, tmp_path, name):
 
 
 @pytest.mark.parametrize("name", G.names("a08_") + G.names("a09_"))
-def test_a08_a09_scene(oracle_lib, tmp_path, name):
+def test_a08_a09_scene(ref_lib, tmp_path, name):
     fx = G.load(name)
     P = fx["params"]
     path = G.materialize_scene(fx["tree"], [], tmp_path)
     scene = OH.loadScene(path, P["cols"], P["rows"], assignment=P["assignment"])
     if P["assignment"] == 8:
-        acu, pix, st = OR.a08_render(oracle_lib, scene, P["cols"], P["rows"], P["n_slabs"])
+        acu, pix, st = OR.a08_render(ref_lib, scene, P["cols"], P["rows"], P["n_slabs"])
     else:
-        acu, pix, st = OR.a09_render(oracle_lib, scene, P["cols"], P["rows"], P["rpp"], P["n_slabs"])
+        acu, pix, st = OR.a09_render(ref_lib, scene, P["cols"], P["rows"], P["rpp"], P["n_slabs"])
     _eq(acu, fx["acu"], "acu")
     _eq(pix, fx["pixels"], "pixels")
     _eq(st["pois"]["matId"].astype(np.int32), fx["matid"], "hit material ids")
@@ -60,17 +60,17 @@ def test_a08_a09_scene(oracle_lib, tmp_path, name):
 
 
 @pytest.mark.parametrize("name", G.names("mol_"))
-def test_molecule(oracle_lib, name):
+def test_molecule(ref_lib, name):
     fx = G.load(name)
     P = fx["params"]
     mol = OH.parsePDB(G.pdb_text(fx["serial"], fx["elem"], fx["xyz"]))
     assert mol["size"] == P["size"]
-    _eq(OR.a02_render(oracle_lib, mol, P["cols"], P["rows"]), fx["a02_pixels"], "A02 pixels")
-    p3, r3 = OR.a03_render(oracle_lib, mol, P["cols"], P["rows"])
+    _eq(OR.a02_render(ref_lib, mol, P["cols"], P["rows"]), fx["a02_pixels"], "A02 pixels")
+    p3, r3 = OR.a03_render(ref_lib, mol, P["cols"], P["rows"])
     _eq(p3, fx["a03_pixels"], "A03 pixels")
     _eq(r3["mint"], fx["a03_mint"], "A03 ray mint")
     for n, g in zip(P["slabs"], fx["grids"]):
-        p7, r7, prep = OR.a07_render(oracle_lib, P["cols"], P["rows"], n, molData=mol)
+        p7, r7, prep = OR.a07_render(ref_lib, P["cols"], P["rows"], n, molData=mol)
         m = prep["mol"]
         assert (int(m["box"][-1]), G.digest(m["box"]), G.digest(m["atoms"]), G.digest(m["index"])) == (g["refs"], g["box"], g["prim"], g["index"])
         _eq(p7, fx["a07_pixels_n%d" % n], "A07 molTrace pixels n=%d" % n)
@@ -78,7 +78,7 @@ def test_molecule(oracle_lib, name):
 
 
 @pytest.mark.parametrize("name", G.names("tri_"))
-def test_mesh(oracle_lib, tmp_path, name):
+def test_mesh(ref_lib, tmp_path, name):
     fx = G.load(name)
     P = fx["params"]
     m = G.meshes_of(fx)[0]
@@ -91,28 +91,28 @@ def test_mesh(oracle_lib, tmp_path, name):
         assert (int(box[-1]), G.digest(box.astype(np.uint32)), G.digest(OH.to_f32(pos)), G.digest(OH.to_f32(nor))) == (
             g["refs"], g["box"], g["prim"], g["normal"])
     for n in P["slabs"]:
-        p7, r7, _ = OR.a07_render(oracle_lib, P["cols"], P["rows"], n, meshData=md)
+        p7, r7, _ = OR.a07_render(ref_lib, P["cols"], P["rows"], n, meshData=md)
         _eq(p7, fx["a07_pixels_n%d" % n], "A07 meshTrace pixels n=%d" % n)
         _eq(r7["maxt"], fx["a07_maxt_n%d" % n], "A07 meshTrace maxt n=%d" % n)
     if P.get("with_mol"):
         mol = OH.parsePDB(G.pdb_text(fx["both_serial"], fx["both_elem"], fx["both_xyz"]))
-        pb, rb, _ = OR.a07_render(oracle_lib, P["cols"], P["rows"], 5, molData=mol, meshData=md)
+        pb, rb, _ = OR.a07_render(ref_lib, P["cols"], P["rows"], 5, molData=mol, meshData=md)
         _eq(pb, fx["both_pixels"], "A07 computeBoth pixels")
         _eq(rb["maxt"], fx["both_maxt"], "A07 computeBoth maxt")
 
 
-def test_a01(oracle_lib):
+def test_a01(ref_lib):
     fx = G.load("a01")
     for cols, rows in fx["params"]["sizes"]:
-        _eq(OR.a01_render(oracle_lib, cols, rows), fx["pixels_%dx%d" % (cols, rows)], "A01 %dx%d" % (cols, rows))
+        _eq(OR.a01_render(ref_lib, cols, rows), fx["pixels_%dx%d" % (cols, rows)], "A01 %dx%d" % (cols, rows))
 
 
-def test_struct_size_probes(oracle_lib):
+def test_struct_size_probes(ref_lib):
     """sizeofRay / sizeofPoi (A10/code.cl:440-446): the layouts every buffer is sized by."""
-    assert oracle_lib.a10_sizeofRay() == 48 and oracle_lib.a10_sizeofPoi() == 64
-    assert oracle_lib.a08_sizeofRay() == 48 and oracle_lib.a08_sizeofPoi() == 48
-    assert oracle_lib.a09_sizeofRay() == 48 and oracle_lib.a09_sizeofPoi() == 48
-    assert oracle_lib.a03_sizeofRay() == 48 and oracle_lib.a07_sizeofRay() == 48
+    assert ref_lib.a10_sizeofRay() == 48 and ref_lib.a10_sizeofPoi() == 64
+    assert ref_lib.a08_sizeofRay() == 48 and ref_lib.a08_sizeofPoi() == 48
+    assert ref_lib.a09_sizeofRay() == 48 and ref_lib.a09_sizeofPoi() == 48
+    assert ref_lib.a03_sizeofRay() == 48 and ref_lib.a07_sizeofRay() == 48
 
 
 def test_instrumented_build_is_arithmetic_neutral(tmp_path):
@@ -130,3 +130,50 @@ def test_instrumented_build_is_arithmetic_neutral(tmp_path):
         res.append((st.acu.copy(), st.seeds.copy(), pix.copy()))
     for a, b in zip(*res):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("name", G.names("a10_"))
+def test_port_equals_reference_kernels(tmp_path, name):
+    """The plain-C restatement of the Assignment-10 kernels (oracle/rt_oracle.c, kind "port") against the fixtures
+    the reference's own kernel text produced: same accumulation image, seed buffer, pixels and ray counts, bit for bit."""
+    port = OR.load_port()
+    assert port.kind == "port"
+    fx = G.load(name)
+    P = fx["params"]
+    scene = OH.loadScene(G.materialize_scene(fx["tree"], G.meshes_of(fx), tmp_path), P["cols"], P["rows"], assignment=10)
+    prep = OR.prepare_a10(scene, 1)
+    total = P["cols"] * P["rows"] * P["rpp"]
+    st = OR.A10State(total, OR.make_seeds(total, P["seed"]))
+    port.a10_initAcu(st.acu, total)
+    for p in range(P["passes"]):
+        pix = OR.a10_execute_render(port, st, prep, fx["cam16"], P["cols"], P["rows"], P["rpp"], scene["focal_length"], scene["lens_diameter"])
+        acc = np.zeros((P["cols"] * P["rows"], 4), np.float32)
+        for k in range(P["rpp"]):
+            acc += st.acu.reshape(-1, P["rpp"], 4)[:, k]
+        _eq(acc, fx["accum"][p], "accumulation image, pass %d" % p)
+        _eq(st.seeds, fx["seeds_after"][p], "seed buffer after pass %d" % p)
+        _eq(pix, fx["pixels"][p], "pixels, pass %d" % p)
+        assert [st.n_closest, st.n_any] == list(fx["counts"][p])
+
+
+def test_port_rpp1_and_row_tiles_equal_reference(tmp_path):
+    """rays_per_pixel == 1 (serial seeds[col] order, Q7) and the row-tile entry of the port against the reference build."""
+    if not OR.have_reference():
+        pytest.skip("oracle/_ref not built")
+    ref, port = OR.load_reference(), OR.load_port()
+    fx = G.load("a10_cornell_teapot3")
+    P = fx["params"]
+    scene = OH.loadScene(G.materialize_scene(fx["tree"], G.meshes_of(fx), tmp_path), P["cols"], P["rows"], assignment=10)
+    prep = OR.prepare_a10(scene, 1)
+    cols, rows = P["cols"], P["rows"]
+    out = []
+    for lib in (ref, port):
+        st = OR.A10State(cols * rows, OR.make_seeds(cols * rows, 3))
+        lib.a10_initAcu(st.acu, st.total)
+        pix = OR.a10_execute_render(lib, st, prep, fx["cam16"], cols, rows, 1, scene["focal_length"], scene["lens_diameter"], serial_init=True)
+        st2 = OR.A10State(cols * 5 * 4, OR.make_seeds(cols * 5 * 4, 4))
+        lib.a10_initAcu(st2.acu, st2.total)
+        OR.a10_execute_render(lib, st2, prep, fx["cam16"], cols, rows, 4, scene["focal_length"], scene["lens_diameter"], row0=7, nrows=5)
+        out.append((st.acu.copy(), st.seeds.copy(), pix.copy(), st2.acu.copy(), st2.seeds.copy()))
+    for a, b in zip(*out):
+        assert a.tobytes() == b.tobytes()
