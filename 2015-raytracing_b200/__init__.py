@@ -13,9 +13,9 @@ The directory name is not a valid Python identifier; import it with
 from . import lib  # noqa: F401  (fails loudly when librt2015.so is missing)
 from . import assignments, multi  # noqa: F401
 from .host import (  # noqa: F401
-    Bounds, Camera, Light, Mesh, Renderer, Vec3, bounds2AABB, loadScene, parseMeshJSON, parsePDB,
+    Bounds, Camera, Light, Mesh, Renderer, Vec3, bounds2AABB, loadScene, parseMeshJSON, parseMeshJSON_native, parsePDB, parsePDB_native,
     splitMaterialData, splitMeshData, splitMolData, splitSphereData, splitTriangleData, write_png,
 )
 
-__all__ = ["lib", "multi", "assignments", "Bounds", "Camera", "Light", "Mesh", "Renderer", "Vec3", "bounds2AABB", "loadScene", "parseMeshJSON",
+__all__ = ["lib", "multi", "assignments", "Bounds", "Camera", "Light", "Mesh", "Renderer", "Vec3", "bounds2AABB", "loadScene", "parseMeshJSON", "parseMeshJSON_native", "parsePDB_native",
            "parsePDB", "splitMaterialData", "splitMeshData", "splitMolData", "splitSphereData", "splitTriangleData", "write_png"]

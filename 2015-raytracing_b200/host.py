@@ -217,6 +217,54 @@ def parseMeshJSON(jsonFileName):
             "normals": np.ascontiguousarray(normals), "tCoords": None}
 
 
+def parseMeshJSON_native(source):
+    """parseMeshJSON through the library's native parser (rt_parse_mesh_json): `source` is a file name or the JSON
+    text as bytes.  Same result object as :func:`parseMeshJSON`, ~an order of magnitude faster on big meshes."""
+    if isinstance(source, (bytes, bytearray)):
+        text = bytes(source)
+    else:
+        with open(source, "rb") as f:
+            text = f.read()
+    md = L.MeshData()
+    rc = L.dll.rt_parse_mesh_json(text, len(text), C.byref(md))
+    if rc != 0:
+        raise ValueError("parseMeshJSON: malformed model (rt_parse_mesh_json returned %d)" % rc)
+    try:
+        nt, nm = int(md.n_triangles), int(md.n_materials)
+        pos = np.ctypeslib.as_array(md.positions, shape=(max(nt, 1) * 9,))[:nt * 9].reshape(nt, 9).copy()
+        nor = np.ctypeslib.as_array(md.normals, shape=(max(nt, 1) * 9,))[:nt * 9].reshape(nt, 9).copy()
+        idx = np.ctypeslib.as_array(md.material_indices, shape=(max(nt, 1),))[:nt].astype(np.uint32)
+        mats = [float(v) for v in np.ctypeslib.as_array(md.materials, shape=(max(nm, 1) * 4,))[:nm * 4]]
+        b = Bounds(list(md.bounds_min), list(md.bounds_max))
+    finally:
+        L.dll.rt_mesh_data_free(C.byref(md))
+    return {"nTriangles": nt, "nMaterials": nm, "materialIndices": idx, "materials": mats, "bounds": b, "positions": pos, "normals": nor,
+            "tCoords": None}
+
+
+def parsePDB_native(text):
+    """parsePDB through the library's native parser (rt_parse_pdb); same result object as :func:`parsePDB`."""
+    raw = text.encode("latin-1") if isinstance(text, str) else bytes(text)
+    md = L.MolData()
+    rc = L.dll.rt_parse_pdb(raw, len(raw), C.byref(md))
+    if rc != 0:
+        raise ValueError("parsePDB: unsupported record (rt_parse_pdb returned %d)" % rc)
+    try:
+        nr, ne = int(md.n_records), int(md.n_elements)
+        ad = np.ctypeslib.as_array(md.atom_data, shape=(max(nr, 1) * 4,))[:nr * 4].copy()
+        atomData = []
+        for i in range(nr):
+            atomData += [int(ad[4 * i]), float(ad[4 * i + 1]), float(ad[4 * i + 2]), float(ad[4 * i + 3])]
+        colorData = [float(v) for v in np.ctypeslib.as_array(md.color_data, shape=(max(ne, 1) * 4,))[:ne * 4]]
+        colorData = [int(v) if i % 4 == 3 else v for i, v in enumerate(colorData)]
+        radiusData = [float(v) for v in np.ctypeslib.as_array(md.radius_data, shape=(max(ne, 1),))[:ne]]
+        out = {"size": int(md.size), "atomData": atomData, "colorData": colorData, "radiusData": radiusData,
+               "bounds": Bounds(list(md.bounds_min), list(md.bounds_max))}
+    finally:
+        L.dll.rt_mol_data_free(C.byref(md))
+    return out
+
+
 def _f32round(a):
     return a.astype(np.float32).astype(np.float64)
 

@@ -37,6 +37,20 @@ class MeshXform(C.Structure):
                 ("translate", C.c_double * 3)]
 
 
+class MeshData(C.Structure):
+    """rt_mesh_data."""
+    _fields_ = [("n_triangles", C.c_uint), ("n_materials", C.c_uint), ("positions", C.POINTER(C.c_double)), ("normals", C.POINTER(C.c_double)),
+                ("material_indices", C.POINTER(C.c_uint)), ("materials", C.POINTER(C.c_double)), ("bounds_min", C.c_double * 3),
+                ("bounds_max", C.c_double * 3)]
+
+
+class MolData(C.Structure):
+    """rt_mol_data."""
+    _fields_ = [("size", C.c_uint), ("n_records", C.c_uint), ("n_elements", C.c_uint), ("atom_data", C.POINTER(C.c_double)),
+                ("color_data", C.POINTER(C.c_double)), ("radius_data", C.POINTER(C.c_double)), ("bounds_min", C.c_double * 3),
+                ("bounds_max", C.c_double * 3)]
+
+
 class RenderOpts(C.Structure):
     """rt_render_opts."""
     _fields_ = [("cols", U), ("rows", U), ("rays_per_pixel", U), ("depth", U), ("focal_length", F), ("lens_rad", F),
@@ -92,6 +106,10 @@ _SIGS = {
     "rt_a09_triangleShadowTrace": ([P, U, P, P, P, P, U], I),
     "rt_a09_sceneRender": ([P, P, P, P, P, U], I),
     "rt_a09_copyToPixel": ([P, P, P, F, U, U], I),
+    "rt_parse_mesh_json": ([C.c_char_p, Z, C.POINTER(MeshData)], I),
+    "rt_mesh_data_free": ([C.POINTER(MeshData)], None),
+    "rt_parse_pdb": ([C.c_char_p, Z, C.POINTER(MolData)], I),
+    "rt_mol_data_free": ([C.POINTER(MolData)], None),
     "rt_grid_build_spheres": ([P, P, P, U, P, P, U, C.POINTER(Grid)], I),
     "rt_grid_build_triangles": ([P, P, P, P, U, P, P, U, C.POINTER(MeshXform), C.POINTER(Grid)], I),
     "rt_grid_release": ([P, C.POINTER(Grid)], I),

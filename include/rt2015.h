@@ -177,6 +177,30 @@ int rt_grid_build_triangles(rt_ctx*, const double* pos9, const double* nor9, con
                             rt_grid* out);
 int rt_grid_release(rt_ctx*, rt_grid* g);
 
+/* Native fast paths of the two loaders that feed the grid build (host code; the library allocates the arrays, release
+ * them with the matching *_free).  Results equal the JavaScript loaders number for number, including gl-matrix's
+ * Float32Array rounding of transformed vertices (A10/lib/gl-matrix.js:79-80). */
+typedef struct {
+    unsigned n_triangles, n_materials;
+    double* positions;            /* 9 per triangle */
+    double* normals;              /* 9 per triangle */
+    unsigned* material_indices;   /* 1 per triangle */
+    double* materials;            /* 4 per material (diffuseReflectance) */
+    double bounds_min[3], bounds_max[3];
+} rt_mesh_data;
+int rt_parse_mesh_json(const char* text, size_t len, rt_mesh_data* out);    /* parseMeshJSON, A10/tri/meshDataVersion1.js:12-78 */
+void rt_mesh_data_free(rt_mesh_data* d);
+typedef struct {
+    unsigned size;                /* atoms.length = largest serial (may exceed n_records: quirk Q13) */
+    unsigned n_records, n_elements;
+    double* atom_data;            /* 4 per record: element index, x, y, z */
+    double* color_data;           /* 4 per element */
+    double* radius_data;          /* 1 per element */
+    double bounds_min[3], bounds_max[3];
+} rt_mol_data;
+int rt_parse_pdb(const char* text, size_t len, rt_mol_data* out);           /* parsePDB, A10/mol/pdbParserV1.js:2-85 */
+void rt_mol_data_free(rt_mol_data* d);
+
 /* Scene = what preRender uploads (A10/code.js:1784-1804). */
 int rt_scene_create(rt_ctx*, rt_scene** out);
 int rt_scene_destroy(rt_scene*);

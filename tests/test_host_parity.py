@@ -141,3 +141,98 @@ def test_oracle_fast_grid_build_drops_and_clamps_like_the_loop(monkeypatch):
     for a, b in zip(lit, fast):
         assert np.array_equal(a, b, equal_nan=True)
     assert sorted(set(lit[3].tolist())) == [0, 3]
+
+
+# ------------------------------------------------------------------- native loaders (rt_parse_mesh_json / rt_parse_pdb)
+def _same_mesh(n, o):
+    assert n["nTriangles"] == o["nTriangles"] and n["nMaterials"] == o["nMaterials"]
+    assert np.array_equal(np.asarray(n["positions"]).reshape(-1), np.asarray(o["positions"], dtype=np.float64))
+    assert np.array_equal(np.asarray(n["normals"]).reshape(-1), np.asarray(o["normals"], dtype=np.float64))
+    assert list(n["materialIndices"]) == list(o["materialIndices"]) and list(n["materials"]) == list(o["materials"])
+    assert _b(n["bounds"]) == _b(o["bounds"])
+
+
+def test_native_mesh_loader_matches_oracle(rt, tmp_path):
+    """Node transform + fp32 rounding points, indexed mesh, unknown keys, nested values, BOM."""
+    model = _mesh_model(14, 9)
+    p = tmp_path / "m.json"
+    synth.mesh_to_json_file(model, str(p))
+    _same_mesh(rt.parseMeshJSON_native(str(p)), OH.parseMeshJSON(str(p)))
+    text = '\ufeff{"name": "x", "extra": {"a": [1, {"b": null}, "s\\"q"], "t": true}, ' + p.read_text()[1:]
+    q = tmp_path / "m2.json"
+    q.write_text(text, encoding="utf-8")
+    _same_mesh(rt.parseMeshJSON_native(str(q)), OH.parseMeshJSON(str(p)))
+
+
+@pytest.mark.parametrize("name", G.names("tri_"))
+def test_native_mesh_loader_golden_meshes(rt, tmp_path, name):
+    fx = G.load(name)
+    m = G.meshes_of(fx)[0]
+    p = tmp_path / "m.json"
+    p.write_text(G.mesh_json_text(m["positions"], m["normals"], m["materialIndices"], m["materials"]))
+    _same_mesh(rt.parseMeshJSON_native(str(p)), OH.parseMeshJSON(str(p)))
+
+
+def test_native_mesh_loader_rejects_malformed(rt):
+    for bad in (b"", b"{", b'{"meshes": [{"vertexPositions": [1, 2,', b'{"materials": [], "meshes": [], "nodes": [{"modelMatrix": [1, 2], "meshIndices": []}]}',
+                b'{"materials": [], "meshes": [], "nodes": [{"modelMatrix": [0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0], "meshIndices": []}]}'):
+        with pytest.raises(ValueError):
+            rt.parseMeshJSON_native(bad)
+
+
+@pytest.mark.parametrize("name", G.names("mol_"))
+def test_native_pdb_loader_matches_oracle(rt, name):
+    fx = G.load(name)
+    text = G.pdb_text(fx["serial"], fx["elem"], fx["xyz"])
+    o, n = OH.parsePDB(text), rt.parsePDB_native(text)
+    assert n["size"] == o["size"] and list(n["atomData"]) == list(o["atomData"])
+    assert list(n["colorData"]) == list(o["colorData"]) and list(n["radiusData"]) == list(o["radiusData"])
+    assert _b(n["bounds"]) == _b(o["bounds"])
+
+
+def test_native_pdb_loader_serial_gap_and_altloc(rt):
+    text = synth.synth_pdb(n_atoms=80, gap_at=33)
+    lines = text.split("\n")
+    lines.insert(5, lines[4][:16] + "B" + lines[4][17:])     # an altLoc 'B' duplicate: skipped by both
+    text = "\n".join(lines)
+    o, n = OH.parsePDB(text), rt.parsePDB_native(text)
+    assert n["size"] == o["size"] == 81 and list(n["atomData"]) == list(o["atomData"])
+
+
+def test_native_json_numbers_are_correctly_rounded(rt):
+    """The parser's exact fast path (significand < 2^53, |exp10| <= 22) and its strtod fallback against Python's
+    float() (correctly rounded, like JavaScript's number parsing), compared as raw doubles."""
+    import ctypes as C
+    import random
+    random.seed(3)
+    toks = []
+    for _ in range(60000):
+        k = random.random()
+        if k < 0.3:
+            toks.append(repr(random.uniform(-1e3, 1e3)))
+        elif k < 0.45:
+            toks.append("%.6f" % random.uniform(-10, 10))
+        elif k < 0.6:
+            toks.append("%de%d" % (random.randint(-10 ** 15, 10 ** 15), random.randint(-40, 40)))
+        elif k < 0.7:
+            toks.append("%.17g" % random.uniform(-1, 1))
+        elif k < 0.8:
+            toks.append(str(random.randint(-2 ** 62, 2 ** 62)))
+        elif k < 0.9:
+            toks.append("%.3e" % random.uniform(-1e30, 1e30))
+        else:
+            toks.append(random.choice(["0", "-0", "-0.0", "1e22", "1e23", "9007199254740993", "9007199254740992", "0.1", "1E5",
+                                       "12345678901234567890123", "-0.000001", "5e-324", "1.7976931348623157e308", "2.2250738585072014e-308",
+                                       "1e-22", "1e-23", "123456789012345678e-25"]))
+    n = len(toks) - len(toks) % 4
+    toks = toks[:n]
+    mats = ",".join('{"diffuseReflectance":[%s]}' % ",".join(toks[i:i + 4]) for i in range(0, n, 4))
+    raw = ('{"materials":[%s],"meshes":[]}' % mats).encode()
+    md = rt.lib.MeshData()
+    assert rt.lib.dll.rt_parse_mesh_json(raw, len(raw), C.byref(md)) == 0
+    try:
+        got = np.ctypeslib.as_array(md.materials, shape=(n,)).copy()
+    finally:
+        rt.lib.dll.rt_mesh_data_free(C.byref(md))
+    want = np.array([float(t) for t in toks])
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
