@@ -9,7 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "rt2015.h")
-DECL = re.compile(r"^\s*(?:int|unsigned|void\s*\*|const\s+char\s*\*)\s*(rt_[A-Za-z0-9_]+)\s*\(", re.M)
+DECL = re.compile(r"^\s*(?:int|unsigned|void\s*\*|void|const\s+char\s*\*)\s*(rt_[A-Za-z0-9_]+)\s*\(", re.M)
 
 
 def declared():
