@@ -14,8 +14,9 @@ from . import lib  # noqa: F401  (fails loudly when librt2015.so is missing)
 from . import assignments, multi  # noqa: F401
 from .host import (  # noqa: F401
     Bounds, Camera, Light, Mesh, Renderer, Vec3, bounds2AABB, loadScene, parseMeshJSON, parseMeshJSON_native, parsePDB, parsePDB_native,
-    splitMaterialData, splitMeshData, splitMolData, splitSphereData, splitTriangleData, write_png,
+    splitMaterialData, splitMeshData, splitMolData, splitSphereData, splitTriangleData, slabSplitMeshData, slabSplitMolData, toNormalArray,
+    toPosArray, write_png,
 )
 
 __all__ = ["lib", "multi", "assignments", "Bounds", "Camera", "Light", "Mesh", "Renderer", "Vec3", "bounds2AABB", "loadScene", "parseMeshJSON", "parseMeshJSON_native", "parsePDB_native",
-           "parsePDB", "splitMaterialData", "splitMeshData", "splitMolData", "splitSphereData", "splitTriangleData", "write_png"]
+           "parsePDB", "splitMaterialData", "splitMeshData", "splitMolData", "splitSphereData", "splitTriangleData", "slabSplitMeshData", "slabSplitMolData", "toPosArray", "toNormalArray", "write_png"]

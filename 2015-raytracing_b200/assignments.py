@@ -5,6 +5,9 @@ same buffer preparation, same kernel sequence, one C-ABI launcher per reference 
     A01  compute()                      A01/code.js:166-269
     A02  compute()  (one fused kernel)  A02/code.js:413-573
     A03  compute()  (initTrace+molTrace) A03/code.js:450-598
+    A04  compute / computeTri / computeBoth   A04/code.js:520-606   (brute force, spheres + triangle soup)
+    A05  compute / computeTri / computeBoth   A05/code.js:536-624   (+ bounding boxes)
+    A06  compute / computeTri / computeBoth   A06/code.js:632-729   (1-D slabs along x)
     A07  compute / computeTri / computeBoth   A07/code.js:571-668
     A08  render()                       A08/code.js:1194-1232
     A09  render()                       A09/code.js:1256-1294
@@ -144,6 +147,121 @@ def a03_compute(ctx, molData, cols, rows, timing=False):
     finally:
         f.close()
     return _ret(f, pix, rays[:, 8].copy())
+
+
+def _both_bounds(molData, meshData, who):
+    if molData is None and meshData is None:
+        raise ValueError("%s: need molData and/or meshData" % who)
+    if molData is not None and meshData is not None:
+        bounds = H.Bounds()
+        bounds.merge(molData["bounds"])
+        bounds.merge(meshData["bounds"])
+        return bounds
+    return (molData or meshData)["bounds"]
+
+
+def _mesh_soup(f, meshData):
+    """prepareMeshTrace of A04/A05 (A04/code.js:448-492)."""
+    return (f.upload(H.toPosArray(meshData)), f.upload(H.toNormalArray(meshData)),
+            f.upload(np.ascontiguousarray(meshData["materialIndices"], dtype=np.uint32)),
+            f.upload(np.asarray(meshData["materials"], dtype=np.float64).astype(np.float32)))
+
+
+def a045_compute(ctx, cols, rows, molData=None, meshData=None, boxes=False, timing=False):
+    """compute / computeTri / computeBoth of A04 (``boxes=False``) or A05 (``boxes=True``): initTrace, then the
+    brute-force molTrace and/or meshTrace over one ray buffer.  Returns (pixels, ray maxt per pixel[, ms])."""
+    bounds = _both_bounds(molData, meshData, "a045_compute")
+    a = "rt_a05_" if boxes else "rt_a04_"
+    f = _Frame(ctx, timing)
+    try:
+        cam = _mol_camera(bounds, cols, rows)
+        d_pix, d_rays = f.alloc(4 * cols * rows), f.alloc(RAY_BYTES * cols * rows)
+        mol = mesh = None
+        if molData is not None:
+            atoms, colors = pack_atoms(molData)
+            mol = (f.upload(atoms), f.upload(colors))
+        if meshData is not None:
+            mesh = _mesh_soup(f, meshData)
+        f.begin()
+        if boxes:
+            ctx.call(a + "initTrace", d_pix, L.hptr(cam), d_rays, L.hptr(H.bounds2AABB(bounds)))
+        else:
+            ctx.call(a + "initTrace", d_pix, L.hptr(cam), d_rays)
+        if mol:
+            extra = (L.hptr(H.bounds2AABB(molData["bounds"])),) if boxes else ()
+            ctx.call(a + "molTrace", d_pix, L.hptr(cam), d_rays, int(molData["size"]), mol[0], mol[1], *extra)
+        if mesh:
+            extra = (L.hptr(H.bounds2AABB(meshData["bounds"])),) if boxes else ()
+            ctx.call(a + "meshTrace", d_pix, L.hptr(cam), d_rays, int(meshData["nTriangles"]), mesh[0], mesh[1], mesh[2], mesh[3], *extra)
+        f.end()
+        pix = ctx.download(d_pix, np.uint8, 4 * cols * rows).reshape(rows, cols, 4)
+        rays = ctx.download(d_rays, np.float32, 12 * cols * rows).reshape(-1, 12)
+    finally:
+        f.close()
+    return _ret(f, pix, rays[:, 9].copy())
+
+
+def a04_compute(ctx, cols, rows, molData=None, meshData=None, timing=False):
+    return a045_compute(ctx, cols, rows, molData, meshData, False, timing)
+
+
+def a05_compute(ctx, cols, rows, molData=None, meshData=None, timing=False):
+    return a045_compute(ctx, cols, rows, molData, meshData, True, timing)
+
+
+def a04_raytrace(ctx, molData, cols, rows):
+    """The fused kernel Assignment 4 still carries (A04/code.cl:317-364); its code.js no longer launches it."""
+    f = _Frame(ctx)
+    try:
+        atoms, colors = pack_atoms(molData)
+        d_atoms, d_colors, d_pix = f.upload(atoms), f.upload(colors), f.alloc(4 * cols * rows)
+        cam = _mol_camera(molData["bounds"], cols, rows)
+        ctx.call("rt_a04_raytrace", d_pix, L.hptr(cam), int(molData["size"]), d_atoms, d_colors)
+        pix = ctx.download(d_pix, np.uint8, 4 * cols * rows).reshape(rows, cols, 4)
+    finally:
+        f.close()
+    return pix
+
+
+def a06_compute(ctx, cols, rows, n_slabs=5, molData=None, meshData=None, timing=False):
+    """compute / computeTri / computeBoth of A06: x slabs built on the GPU (rt_slab_build_*), initTrace against the
+    (merged) bounds, then molTrace and/or meshTrace.  Returns (pixels, ray maxt per pixel[, ms])."""
+    bounds = _both_bounds(molData, meshData, "a06_compute")
+    f = _Frame(ctx, timing)
+    grids = []
+    try:
+        cam = _mol_camera(bounds, cols, rows)
+        d_pix, d_rays = f.alloc(4 * cols * rows), f.alloc(RAY_BYTES * cols * rows)
+        mol = mesh = None
+        if molData is not None:
+            g = H.slabSplitMolData(ctx, molData, n_slabs)
+            grids.append(g)
+            # colorData per slab reference (A06/code.js:511-514) = element colour looked up through the reference's element index
+            ids = ctx.download(g.matid, np.uint32, g.n_refs) if g.n_refs else np.zeros(0, np.uint32)
+            col = np.asarray(molData["colorData"], dtype=np.float64).reshape(-1, 4)[ids].astype(np.float32).reshape(-1)
+            mol = (g, f.upload(col) if len(col) else f.alloc(16))
+        if meshData is not None:
+            g = H.slabSplitMeshData(ctx, meshData, n_slabs)
+            grids.append(g)
+            mesh = (g, f.upload(np.asarray(meshData["materials"], dtype=np.float64).astype(np.float32)))
+        f.begin()
+        ctx.call("rt_a06_initTrace", d_pix, L.hptr(cam), d_rays, L.hptr(H.bounds2AABB(bounds)))
+        if mol:
+            g, d_col = mol
+            ctx.call("rt_a06_molTrace", d_pix, L.hptr(cam), d_rays, int(molData["size"]), g.prim, d_col, L.hptr(H.bounds2AABB(molData["bounds"])),
+                     int(n_slabs), g.box_size)
+        if mesh:
+            g, d_col = mesh
+            ctx.call("rt_a06_meshTrace", d_pix, L.hptr(cam), d_rays, int(meshData["nTriangles"]), g.prim, g.normal, g.matid, d_col,
+                     L.hptr(H.bounds2AABB(meshData["bounds"])), int(n_slabs), g.box_size)
+        f.end()
+        pix = ctx.download(d_pix, np.uint8, 4 * cols * rows).reshape(rows, cols, 4)
+        rays = ctx.download(d_rays, np.float32, 12 * cols * rows).reshape(-1, 12)
+    finally:
+        for g in grids:
+            L.dll.rt_grid_release(ctx.h, C.byref(g))
+        f.close()
+    return _ret(f, pix, rays[:, 9].copy())
 
 
 def a07_compute(ctx, cols, rows, n_slabs=2, molData=None, meshData=None, timing=False):

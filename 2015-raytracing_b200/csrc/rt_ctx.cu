@@ -103,7 +103,7 @@ int rt_buffer_fill(rt_ctx* ctx, void* dptr, int byte_value, size_t bytes) {
 
 unsigned rt_struct_size(const char* name, int assignment) {
     if (!name) return 0;
-    if (!strcmp(name, "Ray")) return (assignment == 3 || assignment == 7 || assignment == 8 || assignment == 9 || assignment == 10) ? 48u : 0u;
+    if (!strcmp(name, "Ray")) return (assignment >= 3 && assignment <= 10) ? 48u : 0u;
     if (!strcmp(name, "Poi")) {
         if (assignment == 10) return 64u;
         if (assignment == 8 || assignment == 9) return 48u;

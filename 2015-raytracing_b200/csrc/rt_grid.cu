@@ -33,8 +33,9 @@ __device__ __forceinline__ void jsRange(double vmin, double vmax, double bmin, d
 }
 
 // kind 0: spheres, prim = (cx,cy,cz,r) -> box = c -+ r ;  kind 1: triangles, prim = 9 doubles.
+// dims = 3: n x n x n cells; dims = 1: n slabs along x (Assignment 6), the y / z extents are not looked at.
 __global__ void k_bin(const double* __restrict__ prim, unsigned n_prims, int kind, double bminx, double bminy, double bminz, double bwx,
-                      double bwy, double bwz, int n, CellBox* __restrict__ boxes, unsigned* __restrict__ prim_refs) {
+                      double bwy, double bwz, int n, int dims, CellBox* __restrict__ boxes, unsigned* __restrict__ prim_refs) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_prims) return;
     double mn[3], mx[3];
@@ -55,8 +56,12 @@ __global__ void k_bin(const double* __restrict__ prim, unsigned n_prims, int kin
     }
     CellBox b;
     jsRange(mn[0], mx[0], bminx, bwx, n, b.lo[0], b.hi[0]);
-    jsRange(mn[1], mx[1], bminy, bwy, n, b.lo[1], b.hi[1]);
-    jsRange(mn[2], mx[2], bminz, bwz, n, b.lo[2], b.hi[2]);
+    if (dims == 3) {
+        jsRange(mn[1], mx[1], bminy, bwy, n, b.lo[1], b.hi[1]);
+        jsRange(mn[2], mx[2], bminz, bwz, n, b.lo[2], b.hi[2]);
+    } else {
+        b.lo[1] = b.hi[1] = b.lo[2] = b.hi[2] = 0;
+    }
     unsigned long long c = 1;
     for (int a = 0; a < 3; a++) c *= (b.hi[a] >= b.lo[a]) ? (unsigned long long)(b.hi[a] - b.lo[a] + 1) : 0ull;
     boxes[i] = b;
@@ -257,12 +262,13 @@ struct XformArg {
 
 // Cell-ordered output buffers (what split*Data pushes, then `new Float32Array(...)` rounds).
 __global__ void k_gather_spheres(const unsigned* __restrict__ ref_prim, unsigned n_refs, const double* __restrict__ xyzr,
-                                 const unsigned* __restrict__ id, float4* __restrict__ out, unsigned* __restrict__ out_id) {
+                                 const unsigned* __restrict__ id, int square_radius, float4* __restrict__ out, unsigned* __restrict__ out_id) {
     unsigned r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_refs) return;
     unsigned i = ref_prim[r];
     const double* p = xyzr + 4ull * i;
-    out[r] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)__dmul_rn(p[3], p[3]));   // w = rad*rad, A10/code.js:1602
+    // w = rad*rad, A10/code.js:1602 (A07-A10); the plain radius for the 1-D slabs of A06 (A06/code.js:481)
+    out[r] = make_float4((float)p[0], (float)p[1], (float)p[2], square_radius ? (float)__dmul_rn(p[3], p[3]) : (float)p[3]);
     if (out_id) out_id[r] = id ? id[i] : 0u;
 }
 
@@ -306,13 +312,14 @@ struct Scratch {   // frees everything it owns (stream-ordered) on scope exit
 };
 
 int buildGrid(rt_ctx* ctx, int kind, const double* prim_host, const double* nor_host, const unsigned* id_host, unsigned n_prims,
-              const double bmin[3], const double bmax[3], unsigned n, const rt_mesh_xform* xform, rt_grid* out) {
+              const double bmin[3], const double bmax[3], unsigned n, const rt_mesh_xform* xform, rt_grid* out, int dims = 3) {
     RT_CHECK_CTX(ctx);
     if (!out || !bmin || !bmax || n == 0 || (n_prims && !prim_host)) return RT_ERR_INVALID;
-    if ((unsigned long long)n * n * n > 0x7FFFFFFFull) return rt_fail(ctx, RT_ERR_INVALID, "grid: n_slabs^3 too large");
+    if (dims == 3 && (unsigned long long)n * n * n > 0x7FFFFFFFull) return rt_fail(ctx, RT_ERR_INVALID, "grid: n_slabs^3 too large");
+    if (n > 0x7FFFFFFFu) return rt_fail(ctx, RT_ERR_INVALID, "grid: n_slabs too large");
     memset(out, 0, sizeof *out);
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t cells = (size_t)n * n * n;
+    const size_t cells = dims == 3 ? (size_t)n * n * n : (size_t)n;
     const unsigned per = kind == 0 ? 4 : 9;
     Scratch s(ctx);
     double *d_prim = nullptr, *d_nor = nullptr;
@@ -351,7 +358,7 @@ int buildGrid(rt_ctx* ctx, int kind, const double* prim_host, const double* nor_
 
     if (n_prims) {
         k_bin<<<rt_blocks(n_prims, kBlock), kBlock, 0, ctx->stream>>>(d_prim, n_prims, kind, bmin[0], bmin[1], bmin[2], bw[0], bw[1], bw[2],
-                                                                       (int)n, d_boxes, d_refs);
+                                                                       (int)n, dims, d_boxes, d_refs);
         RT_LAUNCH_CHECK(ctx, "grid_bin");
         k_count<<<rt_blocks(n_prims, kBlock), kBlock, 0, ctx->stream>>>(d_boxes, d_refs, n_prims, n, d_count);
         RT_LAUNCH_CHECK(ctx, "grid_count");
@@ -387,8 +394,8 @@ int buildGrid(rt_ctx* ctx, int kind, const double* prim_host, const double* nor_
     if (kind == 1 && nor_host) RT_CUDA(ctx, cudaMalloc(&out->normal, prim_bytes ? prim_bytes : 16));
     if (n_refs) {
         if (kind == 0) {
-            k_gather_spheres<<<rt_blocks(n_refs, kBlock), kBlock, 0, ctx->stream>>>(d_refprim, n_refs, d_prim, d_id, (float4*)out->prim,
-                                                                                     (unsigned*)out->matid);
+            k_gather_spheres<<<rt_blocks(n_refs, kBlock), kBlock, 0, ctx->stream>>>(d_refprim, n_refs, d_prim, d_id, dims == 3 ? 1 : 0,
+                                                                                     (float4*)out->prim, (unsigned*)out->matid);
         } else {
             XformArg xf;
             memset(&xf, 0, sizeof xf);
@@ -419,6 +426,18 @@ int rt_grid_build_spheres(rt_ctx* ctx, const double* xyzr, const unsigned* id, u
 int rt_grid_build_triangles(rt_ctx* ctx, const double* pos9, const double* nor9, const unsigned* id, unsigned n, const double bmin[3],
                             const double bmax[3], unsigned n_slabs, const rt_mesh_xform* xform, rt_grid* out) {
     return buildGrid(ctx, 1, pos9, nor9, id, n, bmin, bmax, n_slabs, xform, out);
+}
+
+int rt_slab_build_spheres(rt_ctx* ctx, const double* xyzr, const unsigned* id, unsigned n, double x_min, double x_max, unsigned n_slabs,
+                          rt_grid* out) {
+    const double bmin[3] = {x_min, 0.0, 0.0}, bmax[3] = {x_max, 0.0, 0.0};
+    return buildGrid(ctx, 0, xyzr, nullptr, id, n, bmin, bmax, n_slabs, nullptr, out, 1);
+}
+
+int rt_slab_build_triangles(rt_ctx* ctx, const double* pos9, const double* nor9, const unsigned* id, unsigned n, double x_min, double x_max,
+                            unsigned n_slabs, rt_grid* out) {
+    const double bmin[3] = {x_min, 0.0, 0.0}, bmax[3] = {x_max, 0.0, 0.0};
+    return buildGrid(ctx, 1, pos9, nor9, id, n, bmin, bmax, n_slabs, nullptr, out, 1);
 }
 
 int rt_grid_release(rt_ctx* ctx, rt_grid* g) {

@@ -84,7 +84,7 @@ constexpr unsigned kSphereTile = 1024;   // 16 KB of shared memory
 
 struct BruteHit { float t; unsigned i; };
 
-RT_DEV bool interSphereA02(f3 o, f3 d, float a, float4 s, float& t_out) {
+RT_DEV bool interSphereA02(f3 o, f3 d, float a, float mint, float maxt, float4 s, float& t_out) {
     f3 omc = o - mk3(s.x, s.y, s.z);
     float b = 2.0f * dot(omc, d);
     float c = dot(omc, omc) - s.w;   // s.w = r*r, squared once when the tile was staged (same rounding)
@@ -94,13 +94,14 @@ RT_DEV bool interSphereA02(f3 o, f3 d, float a, float4 s, float& t_out) {
     float t0 = (-b - sq) / 2 * a;
     float t1 = (-b + sq) / 2 * a;
     float tmin = fminf(t0, t1), tmax = fmaxf(t0, t1);
-    if (tmin > 0.0f && tmin < RT_INF) { t_out = tmin; return true; }
-    if (tmax > 0.0f && tmax < RT_INF) { t_out = tmax; return true; }
+    if (tmin > mint && tmin < maxt) { t_out = tmin; return true; }
+    if (tmax > mint && tmax < maxt) { t_out = tmax; return true; }
     return false;
 }
 
-// every thread of the block must call this (barriers inside); `live` lanes own a ray with mint = 0, maxt = +inf
-RT_DEV BruteHit bruteForce(bool live, f3 o, f3 d, unsigned s_size, const float4* __restrict__ s_atoms, float4* tile) {
+// every thread of the block must call this (barriers inside); `live` lanes own a ray; (mint, maxt) is the ray's
+// EXCLUSIVE parameter range (0, +inf for a fresh primary ray)
+RT_DEV BruteHit bruteForce(bool live, f3 o, f3 d, float mint, float maxt, unsigned s_size, const float4* __restrict__ s_atoms, float4* tile) {
     BruteHit h;
     h.t = RT_INF;
     h.i = s_size;
@@ -118,7 +119,7 @@ RT_DEV BruteHit bruteForce(bool live, f3 o, f3 d, unsigned s_size, const float4*
 #pragma unroll 4
             for (unsigned j = 0; j < n; j++) {
                 float t;
-                if (interSphereA02(o, d, a, tile[j], t) && t < h.t) { h.t = t; h.i = base + j; }
+                if (interSphereA02(o, d, a, mint, maxt, tile[j], t) && t < h.t) { h.t = t; h.i = base + j; }
             }
         }
     }
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kBlock) k_a02_raytrace(uchar4* pixels, CamArg 
     f3 o, d;
     pinhole(fcam, id, cam, col, row, o, d);
     bool live = id < cam.cols * cam.rows;
-    BruteHit h = bruteForce(live, o, d, s_size, s_atoms, tile);
+    BruteHit h = bruteForce(live, o, d, 0.0f, RT_INF, s_size, s_atoms, tile);
     if (!live) return;
     uchar4 color = make_uchar4(0, 0, 0, 255);
     if (h.i < s_size) color = shadeSphere<false>(cam, o, d, h.t, __ldg(s_atoms + h.i), __ldg(s_colors + h.i));
@@ -179,12 +180,206 @@ __global__ void __launch_bounds__(kBlock) k_a03_molTrace(uchar4* pixels, CamArg 
     RayR ray;
     ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.mint = 0.f; ray.maxt = RT_INF;
     if (live) ray = loadRay(rays + id);
-    // the stored ray always has mint = 0, maxt = +inf here (initTrace wrote it); the kernel reads them
-    // from memory, and so do we, through the same exclusive test bounds
-    BruteHit h = bruteForce(live, ray.o, ray.d, s_size, s_atoms, tile);
+    BruteHit h = bruteForce(live, ray.o, ray.d, ray.mint, ray.maxt, s_size, s_atoms, tile);
     if (!live || h.i >= s_size) return;
     rays[id].mint = h.t;
     pixels[id] = shadeSphere<true>(cam, ray.o, ray.d, h.t, __ldg(s_atoms + h.i), __ldg(s_colors + h.i));
+}
+
+// ---------------------------------------------------------------------------------------
+// A04 / A05 -- brute force over spheres AND over a triangle soup, one ray buffer shared by both
+// passes (A04/code.cl:204-315, A05/code.cl:304-452).  A05 adds the scene box in initTrace and a
+// per-set box test in front of each loop (BOX = true).  Both loops start champ_t at INFINITY and
+// test against the STORED (mint, maxt) exclusively, so the second pass only accepts what is
+// nearer than the first pass's hit.
+//
+// B200 mapping of the triangle loop: like the spheres, every thread of a block reads the same
+// triangle, so triangles are staged through shared memory in tiles -- and staged in the
+// ray-independent form the test starts from (p0, e1 = p1 - p0, e2 = p2 - p0, cross(e2, e1)),
+// computed ONCE per tile by the staging thread with the reference's own operations instead of
+// once per (ray, triangle).  The per-ray part is interTriangleFast's arrangement (sign rejections
+// before the IEEE division, see rt_device.cuh) with the exclusive range test.
+// ---------------------------------------------------------------------------------------
+constexpr unsigned kTriTile = 256;   // 4 float4 per triangle = 16 KB of shared memory
+
+// interTriangle of A04-A07 (A04/code.cl:156-188): exclusive range test.  A04/A05 also test `gamma > 1`, which
+// can only fire together with `gamma + beta > 1` (beta >= 0 there and float addition is monotonic), so the
+// one text serves A04-A07.
+RT_DEV bool interTriangleExcl(f3 o, f3 d, float mint, float maxt, float div, f3 p0, f3 e1, f3 e2, float& beta_o, float& gamma_o, float& t_out) {
+    if (div <= 0) return false;
+    f3 s = o - p0;
+    float nb = dot(cross(s, d), e2);
+    float ngm = dot(cross(s, e1), d);
+    if ((nb < 0.0f || ngm < 0.0f) && div < RT_INF) return false;
+    float idiv = 1.0f / div;
+    float beta = nb * idiv;
+    if (beta < 0.0f || beta > 1.0f) return false;
+    float gamma = ngm * idiv;
+    if (gamma < 0.0f || (gamma + beta) < 0.0f || (gamma + beta) > 1.0f) return false;
+    float t = dot(cross(s, e2), e1) * -idiv;
+    if (!(t > mint && t < maxt)) return false;
+    beta_o = beta;
+    gamma_o = gamma;
+    t_out = t;
+    return true;
+}
+
+struct TriHit { float t, beta, gamma; unsigned i; };
+
+// every thread of the block must call this (barriers inside)
+RT_DEV TriHit bruteForceTriangles(bool live, f3 o, f3 d, float mint, float maxt, unsigned t_size, const float4* __restrict__ t_pos, float4* tile) {
+    TriHit h;
+    h.t = RT_INF;
+    h.i = t_size;
+    h.beta = h.gamma = 0.f;
+    for (unsigned base = 0; base < t_size; base += kTriTile) {
+        unsigned n = min(kTriTile, t_size - base);
+        __syncthreads();
+        for (unsigned j = threadIdx.x; j < n; j += blockDim.x) {
+            const float4* q = t_pos + 3ull * (base + j);
+            float4 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+            f3 p0 = mk3(q0.x, q0.y, q0.z);
+            f3 e1 = mk3(q1.x, q1.y, q1.z) - p0;
+            f3 e2 = mk3(q2.x, q2.y, q2.z) - p0;
+            f3 ng = cross(e2, e1);
+            tile[4 * j] = make_float4(ng.x, ng.y, ng.z, 0.f);
+            tile[4 * j + 1] = make_float4(p0.x, p0.y, p0.z, 0.f);
+            tile[4 * j + 2] = make_float4(e1.x, e1.y, e1.z, 0.f);
+            tile[4 * j + 3] = make_float4(e2.x, e2.y, e2.z, 0.f);
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 2
+            for (unsigned j = 0; j < n; j++) {
+                float4 g = tile[4 * j];
+                float div = dot(mk3(g.x, g.y, g.z), d);
+                if (div <= 0) continue;
+                float4 a = tile[4 * j + 1], b = tile[4 * j + 2], c = tile[4 * j + 3];
+                float t, be, ga;
+                if (interTriangleExcl(o, d, mint, maxt, div, mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), be, ga, t) && t < h.t) {
+                    h.t = t; h.i = base + j; h.beta = be; h.gamma = ga;
+                }
+            }
+        }
+    }
+    return h;
+}
+
+template <bool BOX>
+__global__ void __launch_bounds__(kBlock) k_a045_molTrace(uchar4* pixels, CamArg fcam, Ray* rays, unsigned s_size, const float4* s_atoms,
+                                                          const float4* s_colors, AabbArg bound_a) {
+    __shared__ float4 tile[kSphereTile];
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam = floatToCamera(fcam.v);
+    bool live = id < cam.cols * cam.rows;
+    RayR ray;
+    ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.mint = 0.f; ray.maxt = RT_INF;
+    if (live) ray = loadRay(rays + id);
+    if (BOX && live) live = ray.mint != ray.maxt && interAABB(ray.o, ray.d, toAABB(bound_a)).v;   // A05/code.cl:341-351
+    BruteHit h = bruteForce(live, ray.o, ray.d, ray.mint, ray.maxt, s_size, s_atoms, tile);
+    if (!live || h.i >= s_size) return;
+    rays[id].maxt = h.t;
+    pixels[id] = shadeSphere<true>(cam, ray.o, ray.d, h.t, __ldg(s_atoms + h.i), __ldg(s_colors + h.i));
+}
+
+template <bool BOX>
+__global__ void __launch_bounds__(kBlock) k_a045_meshTrace(uchar4* pixels, CamArg fcam, Ray* rays, unsigned t_size, const float4* t_pos,
+                                                           const float4* t_normal, const unsigned* t_mindex, const float4* m_color,
+                                                           AabbArg bound_a) {
+    __shared__ float4 tile[4 * kTriTile];
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam = floatToCamera(fcam.v);
+    bool live = id < cam.cols * cam.rows;
+    RayR ray;
+    ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 1.f); ray.mint = 0.f; ray.maxt = RT_INF;
+    if (live) ray = loadRay(rays + id);
+    if (BOX && live) live = ray.mint != ray.maxt && interAABB(ray.o, ray.d, toAABB(bound_a)).v;   // A05/code.cl:401-411
+    TriHit h = bruteForceTriangles(live, ray.o, ray.d, ray.mint, ray.maxt, t_size, t_pos, tile);
+    if (!live || h.i >= t_size) return;
+    rays[id].maxt = h.t;
+    float4 n0 = __ldg(t_normal + 3ull * h.i), n1 = __ldg(t_normal + 3ull * h.i + 1), n2 = __ldg(t_normal + 3ull * h.i + 2);
+    f3 nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
+    float shade = cl_clamp(dot(cam.W, nrm), 0.0f, 1.0f);
+    float4 c = __ldg(m_color + __ldg(t_mindex + h.i));
+    pixels[id] = mkPixel(c.x * 255.0f * shade, c.y * 255.0f * shade, c.z * 255.0f * shade);   // m_color * 255.0f * shade, A04/code.cl:311
+}
+
+// ---------------------------------------------------------------------------------------
+// A06 -- 1-D uniform slabs along x (A06/code.cl:336-533): the x axis of the later 3-D DDA.  One
+// thread per pixel; the slab lists are short and the walk has at most n_slabs steps.
+// Spheres carry the RADIUS (c = mad(-r, r, |o-c|^2), A06/code.cl:117) and use the inclusive
+// range test; triangles the exclusive one.  Debug colour = slab number mod 3.
+// ---------------------------------------------------------------------------------------
+RT_DEV bool interSphereA06(f3 o, f3 d, float a_dd, float mint, float maxt, float4 s, float& t_out) {
+    f3 omc = o - mk3(s.x, s.y, s.z);
+    float a = a_dd;
+    float b = 2.0f * dot(omc, d);
+    float c = fmaf(-s.w, s.w, dot(omc, omc));
+    float dis = fmaf(-4.0f * c, a, b * b);
+    if (dis < 0.0f) return false;
+    a = 1.0f / (2.0f * a);
+    dis = sqrtf(dis);
+    float t0 = (-b - dis) * a;
+    float t1 = (-b + dis) * a;
+    float tmin = fminf(t0, t1);
+    float tmax = fmaxf(t0, t1);
+    if (tmin >= mint && tmin <= maxt) { t_out = tmin; return true; }
+    if (tmax >= mint && tmax <= maxt) { t_out = tmax; return true; }
+    return false;
+}
+
+template <int PRIM>
+__global__ void k_a06_trace(uchar4* pixels, CamArg fcam, Ray* rays, const float4* prim, const float4* normals, AabbArg bound_a,
+                            unsigned n_slabs, const unsigned* __restrict__ slab_size) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    Camera cam = floatToCamera(fcam.v);
+    if (id >= cam.cols * cam.rows) return;
+    RayR ray = loadRay(rays + id);
+    if (ray.mint == ray.maxt) return;
+    AABB bound = toAABB(bound_a);
+    AabbHit binter = interAABB(ray.o, ray.d, bound);
+    if (!binter.v) return;
+    Axis ax = ddaAxis(ray.o.x, ray.d.x, binter.tmin, bound.pmin.x, bound.pmax.x, n_slabs);   // A06/code.cl:357-370
+    const float a_dd = (PRIM == PRIM_SPHERE) ? dot(ray.d, ray.d) : 0.f;
+    float champ_t = ray.maxt, champ_b = 0.f, champ_g = 0.f;
+    unsigned champ_i = 0xFFFFFFFFu;
+    int champ_slab = (int)n_slabs;
+    float t = binter.tmin;
+    while (true) {
+        const float mint = t, maxt = ax.t_next;
+        const unsigned end = __ldg(slab_size + ax.slab + 1);
+        for (unsigned i = __ldg(slab_size + ax.slab); i < end; i++) {
+            float ti, be = 0.f, ga = 0.f;
+            bool v;
+            if (PRIM == PRIM_SPHERE) {
+                v = interSphereA06(ray.o, ray.d, a_dd, mint, maxt, __ldg(prim + i), ti);
+            } else {
+                float4 q0 = __ldg(prim + 3ull * i), q1 = __ldg(prim + 3ull * i + 1), q2 = __ldg(prim + 3ull * i + 2);
+                v = interTriangle<false>(ray.o, ray.d, mint, maxt, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
+            }
+            if (v && ti < champ_t) { champ_t = ti; champ_i = i; champ_b = be; champ_g = ga; champ_slab = ax.slab; }
+        }
+        if (champ_slab < (int)n_slabs) break;
+        t = ax.t_next;
+        if (t >= binter.tmax) break;
+        ax.t_next += ax.delta_t;
+        ax.slab += ax.step;
+        if (ax.slab == ax.limit) break;
+    }
+    if (champ_slab >= (int)n_slabs) return;
+    rays[id].maxt = champ_t;
+    float shade;
+    if (PRIM == PRIM_SPHERE) {
+        float4 s = __ldg(prim + champ_i);
+        f3 ipoint = getPoint(ray.o, ray.d, champ_t);
+        shade = cl_clamp(dot(cam.W, normalize(ipoint - mk3(s.x, s.y, s.z))), 0.0f, 1.0f);
+    } else {
+        float4 n0 = __ldg(normals + 3ull * champ_i), n1 = __ldg(normals + 3ull * champ_i + 1), n2 = __ldg(normals + 3ull * champ_i + 2);
+        f3 nrm = normalize(interp(champ_b, champ_g, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
+        shade = cl_clamp(dot(cam.W, nrm), 0.0f, 1.0f);
+    }
+    float s127 = shade * 127.0f;   // fcolor *= shade * 127.0f, A06/code.cl:420-421
+    pixels[id] = mkPixel((float)(champ_slab % 3) * s127, (float)((champ_slab + 1) % 3) * s127, (float)((champ_slab + 2) % 3) * s127);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -417,6 +612,88 @@ int rt_a03_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, un
     if (!n) return RT_OK;
     k_a03_molTrace<<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, s_size, (const float4*)s_atoms, (const float4*)s_colors);
     RT_LAUNCH_CHECK(ctx, "A03 molTrace");
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------------------- A04 - A06
+int rt_a04_initTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays) { return rt_a03_initTrace(ctx, pixels, fcam, rays); }
+int rt_a04_raytrace(rt_ctx* ctx, void* pixels, const float* fcam, unsigned s_size, const void* s_atoms, const void* s_colors) {
+    return rt_a02_raytrace(ctx, pixels, fcam, s_size, s_atoms, s_colors);
+}
+
+static int launchMol045(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms, const void* s_colors,
+                        const float* bound) {
+    RT_CHECK_CTX(ctx);
+    if (!pixels || !fcam || !rays || (s_size && (!s_atoms || !s_colors))) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    AabbArg none;
+    memset(&none, 0, sizeof none);
+    if (bound) k_a045_molTrace<true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, s_size, (const float4*)s_atoms, (const float4*)s_colors, mkAabb(bound));
+    else k_a045_molTrace<false><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, s_size, (const float4*)s_atoms, (const float4*)s_colors, none);
+    RT_LAUNCH_CHECK(ctx, "A04/A05 molTrace");
+    return RT_OK;
+}
+static int launchMesh045(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos, const void* t_normal,
+                         const void* t_mindex, const void* m_color, const float* bound) {
+    RT_CHECK_CTX(ctx);
+    if (!pixels || !fcam || !rays || (t_size && (!t_pos || !t_normal || !t_mindex || !m_color))) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    AabbArg none;
+    memset(&none, 0, sizeof none);
+    if (bound) k_a045_meshTrace<true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, t_size, (const float4*)t_pos, (const float4*)t_normal,
+                                                         (const unsigned*)t_mindex, (const float4*)m_color, mkAabb(bound));
+    else k_a045_meshTrace<false><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, t_size, (const float4*)t_pos, (const float4*)t_normal,
+                                                   (const unsigned*)t_mindex, (const float4*)m_color, none);
+    RT_LAUNCH_CHECK(ctx, "A04/A05 meshTrace");
+    return RT_OK;
+}
+int rt_a04_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms, const void* s_colors) {
+    return launchMol045(ctx, pixels, fcam, rays, s_size, s_atoms, s_colors, nullptr);
+}
+int rt_a04_meshTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos, const void* t_normal,
+                     const void* t_mindex, const void* m_color) {
+    return launchMesh045(ctx, pixels, fcam, rays, t_size, t_pos, t_normal, t_mindex, m_color, nullptr);
+}
+int rt_a05_initTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, const float* bound) {
+    return rt_a07_initTrace(ctx, pixels, fcam, rays, bound);   // same text, A05/code.cl:304-328 = A07/code.cl:311-335
+}
+int rt_a05_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms, const void* s_colors,
+                    const float* bound) {
+    if (!bound) return RT_ERR_INVALID;
+    return launchMol045(ctx, pixels, fcam, rays, s_size, s_atoms, s_colors, bound);
+}
+int rt_a05_meshTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos, const void* t_normal,
+                     const void* t_mindex, const void* m_color, const float* bound) {
+    if (!bound) return RT_ERR_INVALID;
+    return launchMesh045(ctx, pixels, fcam, rays, t_size, t_pos, t_normal, t_mindex, m_color, bound);
+}
+int rt_a06_initTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, const float* bound) {
+    return rt_a07_initTrace(ctx, pixels, fcam, rays, bound);   // A06/code.cl:310-334
+}
+int rt_a06_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms, const void* s_colors,
+                    const float* bound, unsigned n_slabs, const void* slab_size) {
+    RT_CHECK_CTX(ctx);
+    (void)s_size; (void)s_colors;   // the kernel colours by slab number; the material lookup is commented out in the reference
+    if (!pixels || !fcam || !rays || !s_atoms || !bound || !n_slabs || !slab_size) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a06_trace<PRIM_SPHERE><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, (const float4*)s_atoms, nullptr, mkAabb(bound), n_slabs,
+                                              (const unsigned*)slab_size);
+    RT_LAUNCH_CHECK(ctx, "A06 molTrace");
+    return RT_OK;
+}
+int rt_a06_meshTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos, const void* t_normal,
+                     const void* t_mindex, const void* m_color, const float* bound, unsigned n_slabs, const void* slab_size) {
+    RT_CHECK_CTX(ctx);
+    (void)t_size; (void)t_mindex; (void)m_color;
+    if (!pixels || !fcam || !rays || !t_pos || !t_normal || !bound || !n_slabs || !slab_size) return RT_ERR_INVALID;
+    size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
+    if (!n) return RT_OK;
+    k_a06_trace<PRIM_TRIANGLE><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, (const float4*)t_pos, (const float4*)t_normal, mkAabb(bound),
+                                                n_slabs, (const unsigned*)slab_size);
+    RT_LAUNCH_CHECK(ctx, "A06 meshTrace");
     return RT_OK;
 }
 

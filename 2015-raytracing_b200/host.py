@@ -352,8 +352,9 @@ def _d3(v):
 class DeviceGrid:
     """Device-resident output of a split*Data call (cell-ordered primitives + box_size)."""
 
-    def __init__(self, ctx, grid, bounds_aabb):
+    def __init__(self, ctx, grid, bounds_aabb, cells=None):
         self.ctx, self.grid, self.aabb = ctx, grid, np.ascontiguousarray(bounds_aabb, dtype=np.float32)
+        self.cells = cells   # None: n^3 cells; the 1-D slabs of Assignment 6 have n
 
     @property
     def n_refs(self):
@@ -365,7 +366,7 @@ class DeviceGrid:
 
     def box_size(self) -> np.ndarray:
         n = self.n_slabs
-        return self.ctx.download(self.grid.box_size, np.uint32, n * n * n + 1)
+        return self.ctx.download(self.grid.box_size, np.uint32, (n * n * n if self.cells is None else self.cells) + 1)
 
     def prim(self) -> np.ndarray:
         per = 4 if self.grid.kind == 0 else 12
@@ -439,6 +440,57 @@ def splitMolData(ctx, molData, n_slabs) -> "L.Grid":
     ids[:m] = ad[:m, 0].astype(np.uint32)
     rec[:m, 3] = np.asarray(molData["radiusData"], dtype=np.float64)[ids[:m]]
     return _build_spheres(ctx, rec, ids, molData["bounds"], n_slabs)
+
+
+def _mol_records(molData):
+    n = int(molData["size"])
+    ad = np.asarray(molData["atomData"], dtype=np.float64).reshape(-1, 4)
+    rec = np.full((n, 4), np.nan)
+    ids = np.zeros(n, dtype=np.uint32)
+    m = min(n, len(ad))
+    rec[:m, :3] = ad[:m, 1:4]
+    ids[:m] = ad[:m, 0].astype(np.uint32)
+    rec[:m, 3] = np.asarray(molData["radiusData"], dtype=np.float64)[ids[:m]]
+    return rec, ids
+
+
+def slabSplitMolData(ctx, molData, n_slabs) -> "L.Grid":
+    """The slab re-ordering inside prepareMolTrace of Assignment 6 (A06/code.js:456-520): atoms binned along x only;
+    ``grid.prim`` keeps (x, y, z, RADIUS), ``grid.matid`` the element index (the colour record the reference copies
+    per slab reference is ``colorData[4 * matid]``), ``grid.box_size`` the n_slabs + 1 slab limits."""
+    rec, ids = _mol_records(molData)
+    b = molData["bounds"]
+    g = L.Grid()
+    ctx.check(L.dll.rt_slab_build_spheres(ctx.h, L.hptr(rec), L.hptr(ids), len(rec), float(b.min[0]), float(b.max[0]), int(n_slabs), C.byref(g)))
+    return g
+
+
+def slabSplitMeshData(ctx, meshData, n_slabs) -> "L.Grid":
+    """splitData of Assignment 6 (A06/code.js:936-1043): triangles binned by their x extent."""
+    pos9 = np.ascontiguousarray(meshData["positions"], dtype=np.float64).reshape(-1, 9)
+    nor9 = np.ascontiguousarray(meshData["normals"], dtype=np.float64).reshape(-1, 9)
+    ids = np.ascontiguousarray(meshData["materialIndices"], dtype=np.uint32)
+    b = meshData["bounds"]
+    g = L.Grid()
+    ctx.check(L.dll.rt_slab_build_triangles(ctx.h, L.hptr(pos9), L.hptr(nor9), L.hptr(ids), len(pos9), float(b.min[0]), float(b.max[0]),
+                                            int(n_slabs), C.byref(g)))
+    return g
+
+
+def toPosArray(meshData) -> np.ndarray:
+    """A04/code.js:845-870: the triangle soup in input order as float4 vertices, w = 1."""
+    p = np.asarray(meshData["positions"], dtype=np.float64).reshape(-1, 3)
+    out = np.ones((len(p), 4), dtype=np.float32)
+    out[:, :3] = p
+    return out.reshape(-1)
+
+
+def toNormalArray(meshData) -> np.ndarray:
+    """A04/code.js:819-843: vertex normals in input order, w = 0."""
+    p = np.asarray(meshData["normals"], dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((len(p), 4), dtype=np.float32)
+    out[:, :3] = p
+    return out.reshape(-1)
 
 
 def splitMaterialData(scene) -> np.ndarray:

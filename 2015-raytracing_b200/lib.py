@@ -87,6 +87,16 @@ _SIGS = {
     "rt_a02_raytrace": ([P, P, P, U, P, P], I),
     "rt_a03_initTrace": ([P, P, P, P], I),
     "rt_a03_molTrace": ([P, P, P, P, U, P, P], I),
+    "rt_a04_initTrace": ([P, P, P, P], I),
+    "rt_a04_molTrace": ([P, P, P, P, U, P, P], I),
+    "rt_a04_meshTrace": ([P, P, P, P, U, P, P, P, P], I),
+    "rt_a04_raytrace": ([P, P, P, U, P, P], I),
+    "rt_a05_initTrace": ([P, P, P, P, P], I),
+    "rt_a05_molTrace": ([P, P, P, P, U, P, P, P], I),
+    "rt_a05_meshTrace": ([P, P, P, P, U, P, P, P, P, P], I),
+    "rt_a06_initTrace": ([P, P, P, P, P], I),
+    "rt_a06_molTrace": ([P, P, P, P, U, P, P, P, U, P], I),
+    "rt_a06_meshTrace": ([P, P, P, P, U, P, P, P, P, P, U, P], I),
     "rt_a07_initTrace": ([P, P, P, P, P], I),
     "rt_a07_molTrace": ([P, P, P, P, U, P, P, P, P, U, P], I),
     "rt_a07_meshTrace": ([P, P, P, P, U, P, P, P, P, P, U, P], I),
@@ -112,6 +122,8 @@ _SIGS = {
     "rt_mol_data_free": ([C.POINTER(MolData)], None),
     "rt_grid_build_spheres": ([P, P, P, U, P, P, U, C.POINTER(Grid)], I),
     "rt_grid_build_triangles": ([P, P, P, P, U, P, P, U, C.POINTER(MeshXform), C.POINTER(Grid)], I),
+    "rt_slab_build_spheres": ([P, P, P, U, C.c_double, C.c_double, U, C.POINTER(Grid)], I),
+    "rt_slab_build_triangles": ([P, P, P, P, U, C.c_double, C.c_double, U, C.POINTER(Grid)], I),
     "rt_grid_release": ([P, C.POINTER(Grid)], I),
     "rt_scene_create": ([P, PP], I),
     "rt_scene_destroy": ([P], I),

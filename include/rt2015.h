@@ -61,7 +61,7 @@ int rt_buffer_read(rt_ctx* ctx, const void* dptr, size_t offset, size_t bytes, v
 int rt_buffer_fill(rt_ctx* ctx, void* dptr, int byte_value, size_t bytes);
 
 /* sizeofRay / sizeofPoi probe kernels, A10/code.cl:440-446, A10/code.js:1064-1076.
- * name = "Ray" | "Poi"; assignment = 3,7,8,9,10.  Returns 0 for an unknown struct. */
+ * name = "Ray" | "Poi"; assignment = 3..10.  Returns 0 for an unknown struct. */
 unsigned rt_struct_size(const char* name, int assignment);
 
 /* ---- 2. one launcher per reference kernel ------------------------------------------------
@@ -100,6 +100,26 @@ int rt_a02_raytrace(rt_ctx*, void* pixels, const float* fcam, unsigned s_size, c
 int rt_a03_initTrace(rt_ctx*, void* pixels, const float* fcam, void* rays);                             /* A03/code.cl:132-143 */
 int rt_a03_molTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms,
                     const void* s_colors);                                                              /* A03/code.cl:145-187 */
+/* A04-A06: brute force over spheres and over a triangle soup sharing one ray buffer, the
+ * same with bounding boxes, and 1-D slabs along x.  t_pos / t_normal = 3 x float4 per triangle (w ignored). */
+int rt_a04_initTrace(rt_ctx*, void* pixels, const float* fcam, void* rays);                             /* A04/code.cl:204-215 */
+int rt_a04_molTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms,
+                    const void* s_colors);                                                              /* A04/code.cl:217-259 */
+int rt_a04_meshTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos,
+                     const void* t_normal, const void* t_mindex, const void* m_color);                  /* A04/code.cl:261-315 */
+int rt_a04_raytrace(rt_ctx*, void* pixels, const float* fcam, unsigned s_size, const void* s_atoms,
+                    const void* s_colors);                                                              /* A04/code.cl:317-364 (= A02's kernel) */
+int rt_a05_initTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, const float* bound);         /* A05/code.cl:304-328 */
+int rt_a05_molTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms,
+                    const void* s_colors, const float* bound);                                          /* A05/code.cl:330-384 */
+int rt_a05_meshTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos,
+                     const void* t_normal, const void* t_mindex, const void* m_color, const float* bound);   /* A05/code.cl:386-452 */
+int rt_a06_initTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, const float* bound);         /* A06/code.cl:310-334 */
+int rt_a06_molTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms,
+                    const void* s_colors, const float* bound, unsigned n_slabs, const void* slab_size); /* A06/code.cl:336-426; s_atoms.w = RADIUS */
+int rt_a06_meshTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned t_size, const void* t_pos,
+                     const void* t_normal, const void* t_mindex, const void* m_color, const float* bound,
+                     unsigned n_slabs, const void* slab_size);                                          /* A06/code.cl:428-533 */
 int rt_a07_initTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, const float* bound);         /* A07/code.cl:311-335 */
 int rt_a07_molTrace(rt_ctx*, void* pixels, const float* fcam, void* rays, unsigned s_size, const void* s_atoms,
                     const void* s_mindex, const void* m_color, const float* bound, unsigned n_slabs,
@@ -175,6 +195,13 @@ int rt_grid_build_spheres(rt_ctx*, const double* xyzr, const unsigned* id, unsig
 int rt_grid_build_triangles(rt_ctx*, const double* pos9, const double* nor9, const unsigned* id, unsigned n,
                             const double bmin[3], const double bmax[3], unsigned n_slabs, const rt_mesh_xform* xform,
                             rt_grid* out);
+/* 1-D slabs along x = the two splitters of Assignment 6 (prepareMolTrace A06/code.js:456-520, splitData
+ * A06/code.js:936-1043): same binning rule on the x extent only.  The returned rt_grid has box_size[n_slabs + 1];
+ * sphere records keep the RADIUS in w (A06's interSphere squares it itself). */
+int rt_slab_build_spheres(rt_ctx*, const double* xyzr, const unsigned* id, unsigned n, double x_min, double x_max,
+                          unsigned n_slabs, rt_grid* out);
+int rt_slab_build_triangles(rt_ctx*, const double* pos9, const double* nor9, const unsigned* id, unsigned n, double x_min,
+                            double x_max, unsigned n_slabs, rt_grid* out);
 int rt_grid_release(rt_ctx*, rt_grid* g);
 
 /* Native fast paths of the two loaders that feed the grid build (host code; the library allocates the arrays, release

@@ -569,6 +569,86 @@ def splitMolData(molData, n_slabs):
     return pos.reshape(-1), idx, box_size
 
 
+# --------------------------------------------------------------------------- A04-A06 buffers
+def toPosArray(meshData):
+    """A04/code.js:845-870 (= A05/code.js:861-886): triangle soup in input order, w = 1."""
+    p = np.asarray(meshData["positions"], dtype=np.float64).reshape(-1, 3)
+    out = np.ones((len(p), 4), dtype=np.float64)
+    out[:, :3] = p
+    return out.reshape(-1)
+
+
+def toNormalArray(meshData):
+    """A04/code.js:819-843: vertex normals in input order, w = 0."""
+    p = np.asarray(meshData["normals"], dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((len(p), 4), dtype=np.float64)
+    out[:, :3] = p
+    return out.reshape(-1)
+
+
+def _slab_lists(ranges, x_min, x_max, n_slabs):
+    """Common part of A06's two splitters (A06/code.js:456-500, 936-1003): slab k of n along x
+    holds every primitive with floor((x_lo - x_min)/w) <= k <= floor((x_hi - x_min)/w), the low
+    index clamped at 0 only and the high one at n-1 only; input order inside a slab."""
+    w = _div(x_max - x_min, n_slabs)
+    slabs = [[] for _ in range(n_slabs)]
+    for i, (lo_x, hi_x) in enumerate(ranges):
+        lo = _floor(_div(lo_x - x_min, w))
+        if lo < 0:
+            lo = 0.0
+        hi = _floor(_div(hi_x - x_min, w))
+        if hi >= n_slabs:
+            hi = float(n_slabs - 1)
+        for k in _irange(lo, hi):
+            slabs[k].append(i)
+    limits, order, total = [0], [], 0
+    for sl in slabs:
+        total += len(sl)
+        limits.append(total)
+        order.extend(sl)
+    return np.array(limits, dtype=np.uint32), np.array(order, dtype=np.int64)
+
+
+def slabSplitMol(molData, n_slabs):
+    """prepareMolTrace of A06 (A06/code.js:456-520): atoms re-ordered into x slabs.  Returns
+    atomData (x,y,z,RADIUS -- not squared) and colorData per slab reference (float64, before the
+    Float32Array store), slab limits, and the element index per reference.  Records past the end
+    of atomData (3IZ4.pdb, Q13) read `undefined`, bin to NaN and land in no slab."""
+    ad, rd, cd = molData["atomData"], molData["radiusData"], molData["colorData"]
+    recs = []
+    for i in range(molData["size"]):
+        ii = i * 4
+        if ii + 3 < len(ad):
+            atomId, cx, cy, cz = ad[ii], ad[ii + 1], ad[ii + 2], ad[ii + 3]
+            rad = rd[atomId]
+        else:
+            atomId, cx, cy, cz, rad = 0, NAN, NAN, NAN, NAN
+        recs.append((atomId, cx, cy, cz, rad))
+    b = molData["bounds"]
+    limits, order = _slab_lists(((cx - rad, cx + rad) for (_, cx, _cy, _cz, rad) in recs), b.min[0], b.max[0], n_slabs)
+    atoms = np.zeros((len(order), 4), dtype=np.float64)
+    colors = np.zeros((len(order), 4), dtype=np.float64)
+    idx = np.zeros(len(order), dtype=np.uint32)
+    for k, i in enumerate(order):
+        atomId, cx, cy, cz, rad = recs[i]
+        atoms[k] = (cx, cy, cz, rad)
+        colors[k] = cd[atomId * 4:atomId * 4 + 4]
+        idx[k] = atomId
+    return atoms.reshape(-1), colors.reshape(-1), limits, idx
+
+
+def slabSplitMesh(meshData, n_slabs):
+    """splitData of A06 (A06/code.js:936-1043).  Returns posData, normalData (w = 0 padded,
+    float64), indexData, slabSizeData."""
+    pos = np.asarray(meshData["positions"], dtype=np.float64).reshape(-1, 3, 3)
+    xs = pos[:, :, 0]
+    ranges = ((min(min(x[0], x[1]), x[2]), max(max(x[0], x[1]), x[2])) for x in xs.tolist())
+    b = meshData["bounds"]
+    limits, order = _slab_lists(ranges, b.min[0], b.max[0], n_slabs)
+    idx = np.asarray(meshData["materialIndices"], dtype=np.uint32)[order] if len(order) else np.zeros(0, np.uint32)
+    return _gather_tri(meshData["positions"], order), _gather_tri(meshData["normals"], order), idx, limits
+
+
 def splitSphereData(scene, n_slabs):
     """A10/code.js:1554-1641."""
     sph = scene["spheres"]

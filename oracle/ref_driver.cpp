@@ -40,6 +40,15 @@ namespace a02 {
 namespace a03 {
 #include "_ref/a03_code.inc"
 }
+namespace a04 {
+#include "_ref/a04_code.inc"
+}
+namespace a05 {
+#include "_ref/a05_code.inc"
+}
+namespace a06 {
+#include "_ref/a06_code.inc"
+}
 namespace a07 {
 #include "_ref/a07_code.inc"
 }
@@ -57,6 +66,7 @@ static_assert(sizeof(a10::Ray) == 48 && sizeof(a10::Poi) == 64, "A10 layouts (SU
 static_assert(sizeof(a08::Ray) == 48 && sizeof(a08::Poi) == 48, "A08 layouts (SURVEY 8)");
 static_assert(sizeof(a09::Ray) == 48 && sizeof(a09::Poi) == 48, "A09 layouts (SURVEY 8)");
 static_assert(sizeof(a07::Ray) == 48 && sizeof(a10::AABB) == 32, "A07 layouts (SURVEY 8)");
+static_assert(sizeof(a04::Ray) == 48 && sizeof(a05::Ray) == 48 && sizeof(a06::Ray) == 48 && sizeof(a06::AABB) == 32, "A04-A06 layouts");
 
 template <typename AABB_T>
 static inline AABB_T mk_aabb(const float* b) {
@@ -153,6 +163,66 @@ void ref_a03_initTrace(void* pixels, const float* cam, void* rays, uint cols, ui
 void ref_a03_molTrace(void* pixels, const float* cam, void* rays, uint s_size, void* s_atoms, void* s_colors, uint cols, uint rows) {
     float16 c = mk_f16(cam);
     ND2(cols, rows, a03::molTrace((uchar4*)pixels, c, (a03::Ray*)rays, s_size, (float4*)s_atoms, (float4*)s_colors));
+}
+
+// ======================================================================== A04 (brute force, spheres + triangle mesh)
+uint ref_a04_sizeofRay() { uint s; a04::sizeofRay(&s); return s; }
+void ref_a04_initTrace(void* pixels, const float* cam, void* rays, uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    ND2(cols, rows, a04::initTrace((uchar4*)pixels, c, (a04::Ray*)rays));
+}
+void ref_a04_molTrace(void* pixels, const float* cam, void* rays, uint s_size, void* s_atoms, void* s_colors, uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    ND2(cols, rows, a04::molTrace((uchar4*)pixels, c, (a04::Ray*)rays, s_size, (float4*)s_atoms, (float4*)s_colors));
+}
+void ref_a04_meshTrace(void* pixels, const float* cam, void* rays, uint t_size, void* t_pos, void* t_normal, uint* t_mindex, void* m_color,
+                       uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    ND2(cols, rows, a04::meshTrace((uchar4*)pixels, c, (a04::Ray*)rays, t_size, (float3*)t_pos, (float3*)t_normal, t_mindex, (float4*)m_color));
+}
+void ref_a04_raytrace(void* pixels, const float* cam, uint s_size, void* s_atoms, void* s_colors, uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    ND2(cols, rows, a04::raytrace((uchar4*)pixels, c, s_size, (float4*)s_atoms, (float4*)s_colors));
+}
+
+// ======================================================================== A05 (+ bounding boxes)
+uint ref_a05_sizeofRay() { uint s; a05::sizeofRay(&s); return s; }
+void ref_a05_initTrace(void* pixels, const float* cam, void* rays, const float* bound, uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    a05::AABB b = mk_aabb<a05::AABB>(bound);
+    ND2(cols, rows, a05::initTrace((uchar4*)pixels, c, (a05::Ray*)rays, b));
+}
+void ref_a05_molTrace(void* pixels, const float* cam, void* rays, uint s_size, void* s_atoms, void* s_colors, const float* bound,
+                      uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    a05::AABB b = mk_aabb<a05::AABB>(bound);
+    ND2(cols, rows, a05::molTrace((uchar4*)pixels, c, (a05::Ray*)rays, s_size, (float4*)s_atoms, (float4*)s_colors, b));
+}
+void ref_a05_meshTrace(void* pixels, const float* cam, void* rays, uint t_size, void* t_pos, void* t_normal, uint* t_mindex, void* m_color,
+                       const float* bound, uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    a05::AABB b = mk_aabb<a05::AABB>(bound);
+    ND2(cols, rows, a05::meshTrace((uchar4*)pixels, c, (a05::Ray*)rays, t_size, (float3*)t_pos, (float3*)t_normal, t_mindex, (float4*)m_color, b));
+}
+
+// ======================================================================== A06 (1-D slabs along x)
+uint ref_a06_sizeofRay() { uint s; a06::sizeofRay(&s); return s; }
+void ref_a06_initTrace(void* pixels, const float* cam, void* rays, const float* bound, uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    a06::AABB b = mk_aabb<a06::AABB>(bound);
+    ND2(cols, rows, a06::initTrace((uchar4*)pixels, c, (a06::Ray*)rays, b));
+}
+void ref_a06_molTrace(void* pixels, const float* cam, void* rays, uint s_size, void* s_atoms, void* s_colors, const float* bound,
+                      uint n_slabs, uint* slab_size, uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    a06::AABB b = mk_aabb<a06::AABB>(bound);
+    ND2(cols, rows, a06::molTrace((uchar4*)pixels, c, (a06::Ray*)rays, s_size, (float4*)s_atoms, (float4*)s_colors, b, n_slabs, slab_size));
+}
+void ref_a06_meshTrace(void* pixels, const float* cam, void* rays, uint t_size, void* t_pos, void* t_normal, uint* t_mindex, void* m_color,
+                       const float* bound, uint n_slabs, uint* slab_size, uint cols, uint rows) {
+    float16 c = mk_f16(cam);
+    a06::AABB b = mk_aabb<a06::AABB>(bound);
+    ND2(cols, rows, a06::meshTrace((uchar4*)pixels, c, (a06::Ray*)rays, t_size, (float3*)t_pos, (float3*)t_normal, t_mindex, (float4*)m_color, b, n_slabs, slab_size));
 }
 
 // ======================================================================== A07

@@ -38,6 +38,16 @@ _SIGS = {
     "a02_raytrace": [_P, _P, _U, _P, _P, _U, _U],
     "a03_initTrace": [_P, _P, _P, _U, _U],
     "a03_molTrace": [_P, _P, _P, _U, _P, _P, _U, _U],
+    "a04_initTrace": [_P, _P, _P, _U, _U],
+    "a04_molTrace": [_P, _P, _P, _U, _P, _P, _U, _U],
+    "a04_meshTrace": [_P, _P, _P, _U, _P, _P, _P, _P, _U, _U],
+    "a04_raytrace": [_P, _P, _U, _P, _P, _U, _U],
+    "a05_initTrace": [_P, _P, _P, _P, _U, _U],
+    "a05_molTrace": [_P, _P, _P, _U, _P, _P, _P, _U, _U],
+    "a05_meshTrace": [_P, _P, _P, _U, _P, _P, _P, _P, _P, _U, _U],
+    "a06_initTrace": [_P, _P, _P, _P, _U, _U],
+    "a06_molTrace": [_P, _P, _P, _U, _P, _P, _P, _U, _P, _U, _U],
+    "a06_meshTrace": [_P, _P, _P, _U, _P, _P, _P, _P, _P, _U, _P, _U, _U],
     "a07_initTrace": [_P, _P, _P, _P, _U, _U],
     "a07_molTrace": [_P, _P, _P, _U, _P, _P, _P, _P, _U, _P, _U, _U],
     "a07_meshTrace": [_P, _P, _P, _U, _P, _P, _P, _P, _P, _U, _P, _U, _U],
@@ -71,7 +81,7 @@ _SIGS = {
     "a10_sceneRender": [_P, _P, _P, _P, _P, _U],
     "a10_copyToPixel": [_P, _P, _F, _U, _U],
 }
-_SIZEOF = ["a03_sizeofRay", "a07_sizeofRay", "a08_sizeofRay", "a08_sizeofPoi", "a09_sizeofRay", "a09_sizeofPoi",
+_SIZEOF = ["a03_sizeofRay", "a04_sizeofRay", "a05_sizeofRay", "a06_sizeofRay", "a07_sizeofRay", "a08_sizeofRay", "a08_sizeofPoi", "a09_sizeofRay", "a09_sizeofPoi",
            "a10_sizeofRay", "a10_sizeofPoi"]
 
 
@@ -327,6 +337,98 @@ def a03_render(lib, molData, cols, rows):
     lib.a03_initTrace(pix, cam16, rays, cols, rows)
     lib.a03_molTrace(pix, cam16, rays, int(molData["size"]), atoms, colors, cols, rows)
     return pix.reshape(rows, cols, 4), rays
+
+
+def _merged_bounds(molData, meshData):
+    if molData is not None and meshData is not None:
+        bounds = H.Bounds()
+        bounds.merge(molData["bounds"])
+        bounds.merge(meshData["bounds"])
+        return bounds
+    return (molData or meshData)["bounds"]
+
+
+def prepare_a045_mesh(meshData):
+    """prepareMeshTrace of A04/A05 (A04/code.js:448-492): the triangle soup in input order."""
+    return {"size": int(meshData["nTriangles"]), "pos": H.to_f32(H.toPosArray(meshData)), "normal": H.to_f32(H.toNormalArray(meshData)),
+            "index": np.asarray(meshData["materialIndices"], dtype=np.uint32), "colors": H.to_f32(meshData["materials"]),
+            "aabb": H.bounds2AABB(meshData["bounds"])}
+
+
+def a04_render(lib, cols, rows, molData=None, meshData=None):
+    """compute / computeTri / computeBoth of A04 (A04/code.js:520-606): `initTrace`, then brute-force
+    `molTrace` and/or `meshTrace` over one ray buffer.  Returns (pixels, rays)."""
+    cam16 = mol_camera(_merged_bounds(molData, meshData), cols, rows).toFloat32Array()
+    pix = np.zeros((rows * cols, 4), dtype=np.uint8)
+    rays = np.zeros(rows * cols, dtype=RAY)
+    lib.a04_initTrace(pix, cam16, rays, cols, rows)
+    if molData is not None:
+        atoms, colors = pack_atoms(molData)
+        lib.a04_molTrace(pix, cam16, rays, int(molData["size"]), atoms, colors, cols, rows)
+    if meshData is not None:
+        t = prepare_a045_mesh(meshData)
+        lib.a04_meshTrace(pix, cam16, rays, t["size"], t["pos"], t["normal"], t["index"], t["colors"], cols, rows)
+    return pix.reshape(rows, cols, 4), rays
+
+
+def a04_raytrace(lib, molData, cols, rows):
+    """The fused `raytrace` kernel A04 still carries (A04/code.cl:317-364; not launched by its code.js)."""
+    atoms, colors = pack_atoms(molData)
+    cam16 = mol_camera(molData["bounds"], cols, rows).toFloat32Array()
+    pix = np.zeros((rows * cols, 4), dtype=np.uint8)
+    lib.a04_raytrace(pix, cam16, int(molData["size"]), atoms, colors, cols, rows)
+    return pix.reshape(rows, cols, 4)
+
+
+def a05_render(lib, cols, rows, molData=None, meshData=None):
+    """Same three flows with bounding boxes (A05/code.js:536-624): `initTrace` clips the primary ray to the
+    (merged) bounds, each trace kernel first tests its own set's box."""
+    bounds = _merged_bounds(molData, meshData)
+    cam16 = mol_camera(bounds, cols, rows).toFloat32Array()
+    pix = np.zeros((rows * cols, 4), dtype=np.uint8)
+    rays = np.zeros(rows * cols, dtype=RAY)
+    lib.a05_initTrace(pix, cam16, rays, H.bounds2AABB(bounds), cols, rows)
+    if molData is not None:
+        atoms, colors = pack_atoms(molData)
+        lib.a05_molTrace(pix, cam16, rays, int(molData["size"]), atoms, colors, H.bounds2AABB(molData["bounds"]), cols, rows)
+    if meshData is not None:
+        t = prepare_a045_mesh(meshData)
+        lib.a05_meshTrace(pix, cam16, rays, t["size"], t["pos"], t["normal"], t["index"], t["colors"], t["aabb"], cols, rows)
+    return pix.reshape(rows, cols, 4), rays
+
+
+def prepare_a06_mol(molData, n_slabs):
+    """prepareMolTrace, A06/code.js:434-544."""
+    atoms, colors, limits, idx = H.slabSplitMol(molData, n_slabs)
+    return {"size": int(molData["size"]), "atoms": H.to_f32(atoms), "colors": H.to_f32(colors), "index": idx,
+            "box": np.asarray(limits, dtype=np.uint32), "aabb": H.bounds2AABB(molData["bounds"]), "n": int(n_slabs)}
+
+
+def prepare_a06_mesh(meshData, n_slabs):
+    """prepareMeshTrace, A06/code.js:546-603."""
+    pos, nor, idx, limits = H.slabSplitMesh(meshData, n_slabs)
+    return {"size": int(meshData["nTriangles"]), "pos": H.to_f32(pos), "normal": H.to_f32(nor), "index": np.asarray(idx, dtype=np.uint32),
+            "colors": H.to_f32(meshData["materials"]), "box": np.asarray(limits, dtype=np.uint32),
+            "aabb": H.bounds2AABB(meshData["bounds"]), "n": int(n_slabs)}
+
+
+def a06_render(lib, cols, rows, n_slabs=5, molData=None, meshData=None):
+    """compute / computeTri / computeBoth of A06 (A06/code.js:632-729): 1-D slabs along x.
+    Returns (pixels, rays, prep)."""
+    bounds = _merged_bounds(molData, meshData)
+    cam16 = mol_camera(bounds, cols, rows).toFloat32Array()
+    pix = np.zeros((rows * cols, 4), dtype=np.uint8)
+    rays = np.zeros(rows * cols, dtype=RAY)
+    lib.a06_initTrace(pix, cam16, rays, H.bounds2AABB(bounds), cols, rows)
+    prep = {"cam": cam16}
+    if molData is not None:
+        m = prep["mol"] = prepare_a06_mol(molData, n_slabs)
+        lib.a06_molTrace(pix, cam16, rays, m["size"], m["atoms"], m["colors"], m["aabb"], m["n"], m["box"], cols, rows)
+    if meshData is not None:
+        t = prepare_a06_mesh(meshData, n_slabs)
+        prep["mesh"] = t
+        lib.a06_meshTrace(pix, cam16, rays, t["size"], t["pos"], t["normal"], t["index"], t["colors"], t["aabb"], t["n"], t["box"], cols, rows)
+    return pix.reshape(rows, cols, 4), rays, prep
 
 
 def prepare_a07_mol(molData, n_slabs):

@@ -31,6 +31,7 @@ from oracle import refcl as OR  # noqa: E402
 
 REF = "/root/reference"
 A = {1: "Assign01-Sphere_Ray_Tracing", 2: "Assign02-Multi_Sphere_Ray_Tracing", 3: "Assign03-Two_Kernel_Ray_Tracing",
+     4: "Assign04-Triangle_Mesh", 5: "Assign05-Bounding_Box", 6: "Assign06-1D_uniform_slab_acceleration",
      7: "Assign07-3D_uniform_grid_acceleration", 8: "Assign08-Shadow_Tracing", 9: "Assign09-Thin_Lens_Camera", 10: "Assign10-Path_Tracing"}
 
 
@@ -105,6 +106,31 @@ def gen_a089(lib, a, scene_file, cols=64, rows=48, rpp=4):
     print(name, "mean pixel", float(pix[..., :3].mean()), "hits", int((hit >= 0).sum()))
 
 
+def a456_outputs(lib, out, cols, rows, slabs, mol=None, mesh=None, prefix=""):
+    """A04 / A05 (brute force, + boxes) and A06 (x slabs) frames of the same inputs."""
+    p, r = OR.a04_render(lib, cols, rows, molData=mol, meshData=mesh)
+    out[prefix + "a04_pixels"], out[prefix + "a04_maxt"] = p, r["maxt"].copy()
+    p, r = OR.a05_render(lib, cols, rows, molData=mol, meshData=mesh)
+    out[prefix + "a05_pixels"], out[prefix + "a05_maxt"] = p, r["maxt"].copy()
+    if mol is not None and mesh is None:
+        out[prefix + "a04_raytrace"] = OR.a04_raytrace(lib, mol, cols, rows)
+    grids = []
+    for n in slabs:
+        p, r, prep = OR.a06_render(lib, cols, rows, n, molData=mol, meshData=mesh)
+        out[prefix + "a06_pixels_n%d" % n], out[prefix + "a06_maxt_n%d" % n] = p, r["maxt"].copy()
+        g = {"n": n}
+        if "mol" in prep:
+            m = prep["mol"]
+            g["mol"] = {"refs": int(m["box"][-1]), "box": G.digest(m["box"]), "prim": G.digest(m["atoms"]), "colors": G.digest(m["colors"]),
+                        "index": G.digest(m["index"])}
+        if "mesh" in prep:
+            t = prep["mesh"]
+            g["mesh"] = {"refs": int(t["box"][-1]), "box": G.digest(t["box"]), "prim": G.digest(t["pos"]), "normal": G.digest(t["normal"]),
+                         "index": G.digest(t["index"])}
+        grids.append(g)
+    return grids
+
+
 def load_mol(a, fname):
     with open(os.path.join(REF, A[a], "mol", fname), "r") as f:
         serial, elem, xyz = G.describe_pdb(f.read())
@@ -122,8 +148,9 @@ def gen_mol(lib, fname, cols=64, rows=48, slabs=(2, 5)):
         out["a07_pixels_n%d" % n], out["a07_maxt_n%d" % n] = p7, r7["maxt"].copy()
         m = prep["mol"]
         grids.append({"n": n, "refs": int(m["box"][-1]), "box": G.digest(m["box"]), "prim": G.digest(m["atoms"]), "index": G.digest(m["index"])})
+    slab_grids = a456_outputs(lib, out, cols, rows, slabs, mol=mol)
     name = "mol_" + os.path.splitext(fname)[0]
-    G.save(name, params={"cols": cols, "rows": rows, "slabs": list(slabs), "size": int(mol["size"]), "source": fname}, grids=grids,
+    G.save(name, params={"cols": cols, "rows": rows, "slabs": list(slabs), "size": int(mol["size"]), "source": fname}, grids=grids, slab_grids=slab_grids,
            serial=serial.astype(np.int32), elem=elem.astype("U2"), xyz=xyz, **out)
     print(name, "size", mol["size"], "records", len(serial), "refs", [g["refs"] for g in grids])
 
@@ -152,8 +179,11 @@ def gen_tri(lib, fname, cols=64, rows=48, slabs=(2, 10), grid_slabs=(1, 2, 5, 10
         serial, elem, xyz, mol = load_mol(7, with_mol)
         pb, rb, _ = OR.a07_render(lib, cols, rows, 5, molData=mol, meshData=md)
         out.update(both_pixels=pb, both_maxt=rb["maxt"].copy(), both_serial=serial.astype(np.int32), both_elem=elem.astype("U2"), both_xyz=xyz)
+    slab_grids = a456_outputs(lib, out, cols, rows, slabs, mesh=md)
+    if with_mol:   # computeBoth of A04 / A05 / A06
+        a456_outputs(lib, out, cols, rows, (5,), mol=mol, mesh=md, prefix="both_")
     name = "tri_" + os.path.splitext(fname)[0]
-    G.save(name, params=params, grids=grids, **mesh_arrays([mesh]), **out)
+    G.save(name, params=params, grids=grids, slab_grids=slab_grids, **mesh_arrays([mesh]), **out)
     print(name, "triangles", md["nTriangles"], "refs", [g["refs"] for g in grids])
 
 

@@ -16,8 +16,8 @@ import golden_io as G
 pytestmark = pytest.mark.gpu
 
 
-def _grid_digests(rt, ctx, g):
-    d = rt.host.DeviceGrid(ctx, g, np.zeros(8, np.float32))
+def _grid_digests(rt, ctx, g, cells=None):
+    d = rt.host.DeviceGrid(ctx, g, np.zeros(8, np.float32), cells=cells)
     out = {"refs": d.n_refs, "box": G.digest(d.box_size()), "prim": G.digest(d.prim())}
     if g.kind == 1 and g.normal:
         out["normal"] = G.digest(d.normal())
@@ -37,6 +37,42 @@ def test_a01(rt, gpu_ctx):
     for cols, rows in fx["params"]["sizes"]:
         pix = rt.assignments.a01_compute(gpu_ctx, cols, rows)
         assert np.array_equal(pix, fx["pixels_%dx%d" % (cols, rows)])
+
+
+def _same_bits(got, want, what):
+    assert np.array_equal(np.asarray(got).view(np.uint32), np.asarray(want).view(np.uint32)), what
+
+
+def _check_a456(rt, ctx, fx, cols, rows, slabs, mol=None, mesh=None, prefix="", slab_grids=None):
+    """A04 / A05 (brute force, + boxes) and A06 (x slabs built on the GPU) frames, SURVEY.md 8f rank 4."""
+    A = rt.assignments
+    p, maxt = A.a04_compute(ctx, cols, rows, molData=mol, meshData=mesh)
+    _same_bits(maxt, fx[prefix + "a04_maxt"], "A04 hit distance / hit set")
+    assert np.array_equal(p, fx[prefix + "a04_pixels"]), "A04 pixels"
+    p, maxt = A.a05_compute(ctx, cols, rows, molData=mol, meshData=mesh)
+    _same_bits(maxt, fx[prefix + "a05_maxt"], "A05 hit distance / hit set")
+    assert np.array_equal(p, fx[prefix + "a05_pixels"]), "A05 pixels"
+    if mol is not None and mesh is None:
+        assert np.array_equal(A.a04_raytrace(ctx, mol, cols, rows), fx[prefix + "a04_raytrace"]), "A04 raytrace"
+    for k, n in enumerate(slabs):
+        if slab_grids is not None:
+            want = slab_grids[k]
+            if "mol" in want:
+                g = rt.slabSplitMolData(ctx, mol, n)
+                got = _grid_digests(rt, ctx, g, cells=n)
+                rt.lib.dll.rt_grid_release(ctx.h, C.byref(g))
+                assert (got["refs"], got["box"], got["prim"], got["matid"]) == (
+                    want["mol"]["refs"], want["mol"]["box"], want["mol"]["prim"], want["mol"]["index"]), "A06 atom slabs differ at n=%d" % n
+            if "mesh" in want:
+                g = rt.slabSplitMeshData(ctx, mesh, n)
+                got = _grid_digests(rt, ctx, g, cells=n)
+                rt.lib.dll.rt_grid_release(ctx.h, C.byref(g))
+                assert (got["refs"], got["box"], got["prim"], got["normal"], got["matid"]) == (
+                    want["mesh"]["refs"], want["mesh"]["box"], want["mesh"]["prim"], want["mesh"]["normal"], want["mesh"]["index"]), \
+                    "A06 triangle slabs differ at n=%d" % n
+        p, maxt = A.a06_compute(ctx, cols, rows, n, molData=mol, meshData=mesh)
+        _same_bits(maxt, fx[prefix + "a06_maxt_n%d" % n], "A06 hit distance / hit set n=%d" % n)
+        assert np.array_equal(p, fx[prefix + "a06_pixels_n%d" % n]), "A06 pixels n=%d" % n
 
 
 @pytest.mark.parametrize("name", G.names("mol_"))
@@ -59,6 +95,7 @@ def test_molecule(rt, gpu_ctx, name):
         p7, maxt = rt.assignments.a07_compute(gpu_ctx, cols, rows, n, molData=mol)
         assert np.array_equal(maxt.view(np.uint32), fx["a07_maxt_n%d" % n].view(np.uint32)), "hit distance / hit set differs"
         assert np.array_equal(p7, fx["a07_pixels_n%d" % n])
+    _check_a456(rt, gpu_ctx, fx, cols, rows, P["slabs"], mol=mol, slab_grids=fx["slab_grids"])
 
 
 @pytest.mark.parametrize("name", G.names("tri_"))
@@ -81,11 +118,13 @@ def test_mesh(rt, gpu_ctx, tmp_path, name):
         p7, maxt = rt.assignments.a07_compute(gpu_ctx, P["cols"], P["rows"], n, meshData=md)
         assert np.array_equal(maxt.view(np.uint32), fx["a07_maxt_n%d" % n].view(np.uint32))
         assert np.array_equal(p7, fx["a07_pixels_n%d" % n])
+    _check_a456(rt, gpu_ctx, fx, P["cols"], P["rows"], P["slabs"], mesh=md, slab_grids=fx["slab_grids"])
     if P.get("with_mol"):
         mol = rt.parsePDB(G.pdb_text(fx["both_serial"], fx["both_elem"], fx["both_xyz"]))
         pb, maxt = rt.assignments.a07_compute(gpu_ctx, P["cols"], P["rows"], 5, molData=mol, meshData=md)
         assert np.array_equal(maxt.view(np.uint32), fx["both_maxt"].view(np.uint32))
         assert np.array_equal(pb, fx["both_pixels"])
+        _check_a456(rt, gpu_ctx, fx, P["cols"], P["rows"], (5,), mol=mol, mesh=md, prefix="both_")
 
 
 @pytest.mark.parametrize("name", G.names("a08_") + G.names("a09_"))

@@ -75,6 +75,33 @@ def test_molecule(ref_lib, name):
         assert (int(m["box"][-1]), G.digest(m["box"]), G.digest(m["atoms"]), G.digest(m["index"])) == (g["refs"], g["box"], g["prim"], g["index"])
         _eq(p7, fx["a07_pixels_n%d" % n], "A07 molTrace pixels n=%d" % n)
         _eq(r7["maxt"], fx["a07_maxt_n%d" % n], "A07 molTrace maxt n=%d" % n)
+    _check_a456(ref_lib, fx, P["cols"], P["rows"], P["slabs"], mol=mol, slab_grids=fx["slab_grids"])
+
+
+def _check_a456(lib, fx, cols, rows, slabs, mol=None, mesh=None, prefix="", slab_grids=None):
+    """A04 / A05 / A06 frames against the fixture entries make_golden.a456_outputs wrote."""
+    p, r = OR.a04_render(lib, cols, rows, molData=mol, meshData=mesh)
+    _eq(p, fx[prefix + "a04_pixels"], "A04 pixels")
+    _eq(r["maxt"], fx[prefix + "a04_maxt"], "A04 ray maxt")
+    p, r = OR.a05_render(lib, cols, rows, molData=mol, meshData=mesh)
+    _eq(p, fx[prefix + "a05_pixels"], "A05 pixels")
+    _eq(r["maxt"], fx[prefix + "a05_maxt"], "A05 ray maxt")
+    if mol is not None and mesh is None:
+        _eq(OR.a04_raytrace(lib, mol, cols, rows), fx[prefix + "a04_raytrace"], "A04 raytrace")
+    for k, n in enumerate(slabs):
+        p, r, prep = OR.a06_render(lib, cols, rows, n, molData=mol, meshData=mesh)
+        _eq(p, fx[prefix + "a06_pixels_n%d" % n], "A06 pixels n=%d" % n)
+        _eq(r["maxt"], fx[prefix + "a06_maxt_n%d" % n], "A06 ray maxt n=%d" % n)
+        if slab_grids is not None:
+            g = slab_grids[k]
+            if "mol" in g:
+                m = prep["mol"]
+                assert (int(m["box"][-1]), G.digest(m["box"]), G.digest(m["atoms"]), G.digest(m["colors"]), G.digest(m["index"])) == (
+                    g["mol"]["refs"], g["mol"]["box"], g["mol"]["prim"], g["mol"]["colors"], g["mol"]["index"])
+            if "mesh" in g:
+                t = prep["mesh"]
+                assert (int(t["box"][-1]), G.digest(t["box"]), G.digest(t["pos"]), G.digest(t["normal"]), G.digest(t["index"])) == (
+                    g["mesh"]["refs"], g["mesh"]["box"], g["mesh"]["prim"], g["mesh"]["normal"], g["mesh"]["index"])
 
 
 @pytest.mark.parametrize("name", G.names("tri_"))
@@ -94,11 +121,13 @@ def test_mesh(ref_lib, tmp_path, name):
         p7, r7, _ = OR.a07_render(ref_lib, P["cols"], P["rows"], n, meshData=md)
         _eq(p7, fx["a07_pixels_n%d" % n], "A07 meshTrace pixels n=%d" % n)
         _eq(r7["maxt"], fx["a07_maxt_n%d" % n], "A07 meshTrace maxt n=%d" % n)
+    _check_a456(ref_lib, fx, P["cols"], P["rows"], P["slabs"], mesh=md, slab_grids=fx["slab_grids"])
     if P.get("with_mol"):
         mol = OH.parsePDB(G.pdb_text(fx["both_serial"], fx["both_elem"], fx["both_xyz"]))
         pb, rb, _ = OR.a07_render(ref_lib, P["cols"], P["rows"], 5, molData=mol, meshData=md)
         _eq(pb, fx["both_pixels"], "A07 computeBoth pixels")
         _eq(rb["maxt"], fx["both_maxt"], "A07 computeBoth maxt")
+        _check_a456(ref_lib, fx, P["cols"], P["rows"], (5,), mol=mol, mesh=md, prefix="both_")
 
 
 def test_a01(ref_lib):
@@ -113,6 +142,7 @@ def test_struct_size_probes(ref_lib):
     assert ref_lib.a08_sizeofRay() == 48 and ref_lib.a08_sizeofPoi() == 48
     assert ref_lib.a09_sizeofRay() == 48 and ref_lib.a09_sizeofPoi() == 48
     assert ref_lib.a03_sizeofRay() == 48 and ref_lib.a07_sizeofRay() == 48
+    assert ref_lib.a04_sizeofRay() == 48 and ref_lib.a05_sizeofRay() == 48 and ref_lib.a06_sizeofRay() == 48
 
 
 def test_instrumented_build_is_arithmetic_neutral(tmp_path):
