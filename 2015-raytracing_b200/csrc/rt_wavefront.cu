@@ -831,6 +831,26 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_coop(c
 // ---------------------------------------------------------------------------------------
 constexpr int kCandCap = 64;
 
+// Software prefetch (exactness-neutral).  ncu attributes most of the walkers' stall samples to the first use of a
+// face-vector / (p0,e1,e2) record that was requested only when the pair list reached it (profiles/), so two hints
+// were tried on B200 at the full config (base 6076 Mrays/s):
+//   RT_PF_PE: when a reference survives the cull, request its (p0,e1,e2) record -- it is read by ANOTHER lane once
+//             32 survivors have been collected.                         L1: 6119, L2: 6115 Mrays/s  -> on (L1)
+//   RT_PF_NG: when a lane enters a non-empty cell, request the lines of that cell's face vectors right away.
+//             L1: 5895, L2: 5897 Mrays/s (the extra instructions in the step loop cost more than the hint saves) -> off
+// 0 = off, 1 = into L1, 2 = into L2.
+#ifndef RT_PF_NG
+#define RT_PF_NG 0
+#endif
+#ifndef RT_PF_PE
+#define RT_PF_PE 1
+#endif
+template <int LEVEL>
+RT_DEV void prefetchLine(const void* p) {
+    if (LEVEL == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    else if (LEVEL == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 template <int PRIM, bool ANY>
 __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w,
                                                                                unsigned n, int qslot) {
@@ -923,6 +943,16 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
         }
     };
 
+    // face vectors of the cell just entered: at most 4 lines of 8 records
+    auto prefetchCell = [&]() {
+        if (PRIM == PRIM_TRIANGLE && RT_PF_NG) {
+            unsigned a = f.i & ~7u;
+#pragma unroll
+            for (int k = 0; k < 4; k++, a += 8)
+                if (a < f.end) prefetchLine<RT_PF_NG>(set.pre_ng + a);
+        }
+    };
+
     while (true) {
         // ---- refill idle lanes from the queue (one atomicAdd per warp)
         unsigned idle = __ballot_sync(FULL, !have);
@@ -949,6 +979,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
 #else
                     flatEnterMacro(f, g, s_macro, mshift, mn);
 #endif
+                    prefetchCell();
                     have = true;
                 }
             }
@@ -974,6 +1005,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
 #else
                     flatEnterMacro(f, g, s_macro, mshift, mn);
 #endif
+                    prefetchCell();
                 }
             }
         }
@@ -1025,6 +1057,10 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
                 s_cref[wid][pos] = ref;
                 s_cown[wid][pos] = own;
                 s_cdiv[wid][pos] = dv;
+                if (PRIM == PRIM_TRIANGLE && RT_PF_PE) {
+                    prefetchLine<RT_PF_PE>(set.pre_pe + 3 * ref);
+                    prefetchLine<RT_PF_PE>(set.pre_pe + 3 * ref + 2);
+                }
             }
             ncand += __popc(m);
             __syncwarp();

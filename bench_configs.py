@@ -94,6 +94,22 @@ def main():
             emit("2: %s, %d spheres, %dx%d" % (name, mol_p["size"], W, H), W * H, g, cw * ch, c, sphere_tests_per_s=round(tests / (g * 1e-3), 0),
                  fp32_issue_frac=round(tests * 18 / (g * 1e-3) / (info["sm_count"] * 128 * 1.965e9), 3))
 
+    # ---- A04 / A05 / A06 on the shapes their demos use: a molecule and a ~1 k-triangle mesh
+    text = synth.synth_pdb(n_atoms=2000 if args.quick else 9018, gap_at=1000)
+    mol_p, mol_o = rt.parsePDB(text), OH.parsePDB(text)
+    model = synth.synth_mesh(31, 16, seed=2015)
+    md_p, md_o = rt.parseMeshJSON(model), OH.parseMeshJSON(model)
+    for name, gf, cf in (
+            ("A04 computeBoth (brute force)", lambda: A.a04_compute(ctx, W, H, molData=mol_p, meshData=md_p, timing=True),
+             lambda: OR.a04_render(olib, cw, ch, molData=mol_o, meshData=md_o)),
+            ("A05 computeBoth (+ boxes)", lambda: A.a05_compute(ctx, W, H, molData=mol_p, meshData=md_p, timing=True),
+             lambda: OR.a05_render(olib, cw, ch, molData=mol_o, meshData=md_o)),
+            ("A06 computeBoth (x slabs, n 5)", lambda: A.a06_compute(ctx, W, H, 5, molData=mol_p, meshData=md_p, timing=True),
+             lambda: OR.a06_render(olib, cw, ch, 5, molData=mol_o, meshData=md_o))):
+        g = best_gpu(gf, args.reps)
+        c = cpu_time(cf, 1)
+        emit("f4: %s, %d spheres + %d triangles, %dx%d" % (name, mol_p["size"], md_p["nTriangles"], W, H), W * H, g, cw * ch, c)
+
     # ---- config 3: A07 grid primary rays: small mesh and the synthetic 1 M-triangle mesh
     for (mu, mv, ns) in (((31, 16, 10),) if args.quick else ((31, 16, 10), (1000, 500, 128))):
         model = synth.synth_mesh(mu, mv, seed=2015)
