@@ -75,8 +75,8 @@ def test_a06_matches_oracle(rt, gpu_ctx, ref_lib, inputs, flow, use_mol, use_mes
 def test_full_frame_properties(rt, gpu_ctx, inputs):
     """1920x1080, no oracle: (1) with all geometry strictly inside its boxes the bounding boxes of A05 only cull, so
     A05's image and hit distances equal A04's; (2) the fused A04 `raytrace` kernel shows the same spheres as
-    initTrace + molTrace wherever the unclamped shade is in range; (3) A06 hits what A05 hits (same primitives reach
-    the same pixels; the sphere arithmetic differs by its explicit mad, so distances are compared to 1e-4 relative)."""
+    initTrace + molTrace wherever the unclamped shade is in range; (3) A06 finds the same nearest primitive as A05
+    (its sphere arithmetic differs by the explicit mad, so distances are compared to 1e-4 relative)."""
     A = rt.assignments
     W, H = 1920, 1080
     mol, mesh = inputs["mol_p"], inputs["mesh_p"]
@@ -93,9 +93,9 @@ def test_full_frame_properties(rt, gpu_ctx, inputs):
     fused = A.a04_raytrace(gpu_ctx, mol, W, H)
     lit = pm.reshape(-1, 4)[:, :3].sum(axis=1) > 0          # clamped shade > 0 <=> the unclamped one is the same number
     assert np.array_equal(fused.reshape(-1, 4)[lit], pm.reshape(-1, 4)[lit])
+    # both start from the same initTrace (finite maxt = exit of the scene box) and lower maxt to the nearest primitive
     p6, t6 = A.a06_compute(gpu_ctx, W, H, 5, molData=mol, meshData=mesh)
-    prim5 = np.isfinite(t5) & (p5.reshape(-1, 4)[:, :3].sum(axis=1) > 0)
-    prim6 = np.isfinite(t6) & (p6.reshape(-1, 4)[:, :3].sum(axis=1) > 0)
-    assert (prim5 != prim6).mean() < 1e-4
-    both = prim5 & prim6
-    assert np.abs(t5[both] - t6[both]).max() <= 1e-4 * np.abs(t5[both]).max()
+    box = np.isfinite(t5)
+    assert np.array_equal(box, np.isfinite(t6))
+    off = np.abs(t5[box] - t6[box]) > 1e-4 * np.abs(t5[box]).max()
+    assert off.mean() < 1e-4, "A06 and A05 disagree on the nearest primitive of %d pixels" % off.sum()
