@@ -27,7 +27,17 @@ napi_status napi_get_value_uint32(napi_env env, napi_value value, uint32_t* resu
 napi_status napi_get_value_int64(napi_env env, napi_value value, int64_t* result);
 napi_status napi_get_value_bigint_uint64(napi_env env, napi_value value, uint64_t* result, bool* lossless);
 napi_status napi_get_value_string_utf8(napi_env env, napi_value value, char* buf, size_t bufsize, size_t* result);
+napi_status napi_get_value_double(napi_env env, napi_value value, double* result);
 napi_status napi_create_uint32(napi_env env, uint32_t value, napi_value* result);
+napi_status napi_create_int32(napi_env env, int32_t value, napi_value* result);
+napi_status napi_create_double(napi_env env, double value, napi_value* result);
+napi_status napi_create_string_utf8(napi_env env, const char* str, size_t length, napi_value* result);
+napi_status napi_create_object(napi_env env, napi_value* result);
+napi_status napi_get_named_property(napi_env env, napi_value object, const char* utf8name, napi_value* result);
+napi_status napi_has_named_property(napi_env env, napi_value object, const char* utf8name, bool* result);
+napi_status napi_create_arraybuffer(napi_env env, size_t byte_length, void** data, napi_value* result);
+napi_status napi_create_typedarray(napi_env env, napi_typedarray_type type, size_t length, napi_value arraybuffer, size_t byte_offset,
+                                   napi_value* result);
 napi_status napi_create_bigint_uint64(napi_env env, uint64_t value, napi_value* result);
 napi_status napi_is_typedarray(napi_env env, napi_value value, bool* result);
 napi_status napi_get_typedarray_info(napi_env env, napi_value typedarray, napi_typedarray_type* type, size_t* length, void** data,
