@@ -194,7 +194,7 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
     name = {"walk_triangle_closest": "k_walk_pairs<triangle, closest hit>", "walk_triangle_any": "k_walk_pairs<triangle, any hit>",
             "walk_sphere_closest": "k_walk_pairs<sphere, closest hit>", "walk_sphere_any": "k_walk_pairs<sphere, any hit>"}[dom]
     return {"bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": round(d["achieved_gbs"] / peak, 4),
-            "traffic": (int(NCU_TRAFFIC[dom] * (args.cols * args.rows * args.spp / max(args.gpus, 1)) / NCU_TRAFFIC_SLOTS) if dom in NCU_TRAFFIC else None),
+            "traffic": ncu_traffic(dom, args, d["launches_per_step"]),
             "kernel": name, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if measured_peak else "fallback",
             "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "launch_ms": d["launch_ms"],
             "share_of_step": d["share_of_step"], "kernels": per, "step": step,
@@ -202,10 +202,23 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the walker kernels from the committed `ncu --set full`
-# capture of this command at N = 1 (profiles/r1b_walk_full_summary.md: one tile = the whole frame, 530 841 600 slots
-# per launch; mean over the captured launches).  For N > 1 a launch covers 1/N of the slots and the figure is scaled.
-NCU_TRAFFIC = {"walk_triangle_any": 21283724688, "walk_triangle_closest": 21830812956}
-NCU_TRAFFIC_SLOTS = 1920 * 1080 * 256
+# capture of this command at N = 1 (profiles/r1c_walk_full_summary.md, mean over the captured launches).  A launch
+# walks the queue of ONE tile of ONE pipeline stage; at N = 1 the frame is two tiles (412 721 664 + 118 119 936 slots =
+# a quarter of device memory + the rest) and the captured launches belong to the SMALL tile, so the figure is per
+# 118 119 936 slots.  Traffic follows the number of queued rays, hence the slots: a step's total is the figure x
+# (slots of this rank / 118 119 936) x stages (any hit: (1 + depth) x lights, closest hit: 1 + depth), divided over
+# the launches of the step for the per-launch average reported next to `achieved`.  Default workload only.
+NCU_TRAFFIC = {"walk_triangle_any": 22476466064, "walk_triangle_closest": 22222815120}
+NCU_TRAFFIC_SLOTS = 118119936
+NCU_TRAFFIC_WORKLOAD = (1920, 1080, 256, 1000, 500, 128, 2)
+
+
+def ncu_traffic(dom, args, launches_per_step):
+    if dom not in NCU_TRAFFIC or (args.cols, args.rows, args.spp, args.mesh_u, args.mesh_v, args.nslabs, args.lights) != NCU_TRAFFIC_WORKLOAD:
+        return None
+    stages = (1 + args.depth) * (args.lights if dom.endswith("_any") else 1)
+    slots = args.cols * args.rows * args.spp / max(args.gpus, 1)
+    return int(NCU_TRAFFIC[dom] * (slots / NCU_TRAFFIC_SLOTS) * stages / max(launches_per_step, 1))
 
 
 # ------------------------------------------------------------------------------ main

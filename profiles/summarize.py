@@ -84,8 +84,8 @@ def full(tag, title, kernel_filter):
     out = io.StringIO()
     out.write("# %s -- `ncu --set full` of %s\n\n" % (P, title))
     out.write("Command (B200, 1 GPU): `ncu --set full --clock-control none --import-source on --kernel-name regex:%s --launch-skip 24 "
-              "--launch-count 4 -o %s_%s_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (full config, one tile = the whole frame: "
-              "530 841 600 slots per launch).\n\n" % (kernel_filter, P, tag))
+              "--launch-count 4 -o %s_%s_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (full config; the frame is two tiles, 412 721 664 + 118 119 936 "
+              "slots, a launch serves one tile; the captured launches belong to the small tile).\n\n" % (kernel_filter, P, tag))
     n = len(rows) - 2
     i_n = hdr.index('Kernel Name')
     out.write("| metric | unit | " + " | ".join(short(r[i_n]) for r in rows[2:]) + " |\n|---|---|" + "---|" * n + "\n")
