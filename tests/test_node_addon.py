@@ -69,23 +69,23 @@ def test_addon_renders_like_the_ctypes_binding(rt, addon_test, tmp_path):
     L = rt.lib
     cols, rows, rpp = 48, 32, 4
     total = cols * rows * rpp
+    # every host array is bound to a name first: a temporary would be freed (and its memory reused) before the C call reads it
+    f32 = {k: d("in_%s.bin" % k, np.float32) for k in ("bound", "materials", "sbound", "tbound", "l_shadow", "l_scene", "l_light", "cam")}
+    f64 = {k: d("in_%s.bin" % k, np.float64) for k in ("xyzr", "pos9", "nor9", "smin", "smax", "tmin", "tmax")}
     with L.Context(0) as ctx:
         gs, gt = L.Grid(), L.Grid()
-        xyzr, pos9, nor9 = d("in_xyzr.bin", np.float64), d("in_pos9.bin", np.float64), d("in_nor9.bin", np.float64)
         sid, tid = np.array([0], np.uint32), np.array([1, 1], np.uint32)
-        d3 = lambda a: (C.c_double * 3)(*a)   # noqa: E731
-        ctx.check(L.dll.rt_grid_build_spheres(ctx.h, L.hptr(xyzr), L.hptr(sid), 1, d3(d("in_smin.bin", np.float64)), d3(d("in_smax.bin", np.float64)), 1,
-                                              C.byref(gs)))
-        ctx.check(L.dll.rt_grid_build_triangles(ctx.h, L.hptr(pos9), L.hptr(nor9), L.hptr(tid), 2, d3(d("in_tmin.bin", np.float64)),
-                                                d3(d("in_tmax.bin", np.float64)), 1, None, C.byref(gt)))
+        d3 = {k: (C.c_double * 3)(*f64[k]) for k in ("smin", "smax", "tmin", "tmax")}
+        ctx.check(L.dll.rt_grid_build_spheres(ctx.h, L.hptr(f64["xyzr"]), L.hptr(sid), 1, d3["smin"], d3["smax"], 1, C.byref(gs)))
+        ctx.check(L.dll.rt_grid_build_triangles(ctx.h, L.hptr(f64["pos9"]), L.hptr(f64["nor9"]), L.hptr(tid), 2, d3["tmin"], d3["tmax"], 1, None,
+                                                C.byref(gt)))
         scene = C.c_void_p()
         ctx.check(L.dll.rt_scene_create(ctx.h, C.byref(scene)))
-        ctx.check(L.dll.rt_scene_set_bounds(scene, L.hptr(d("in_bound.bin", np.float32))))
-        ctx.check(L.dll.rt_scene_set_materials(scene, L.hptr(d("in_materials.bin", np.float32)), 2))
-        ctx.check(L.dll.rt_scene_add_set(scene, C.byref(gs), L.hptr(d("in_sbound.bin", np.float32)), 0, 0))
-        ctx.check(L.dll.rt_scene_add_set(scene, C.byref(gt), L.hptr(d("in_tbound.bin", np.float32)), 0, 0))
-        ctx.check(L.dll.rt_scene_add_light(scene, L.hptr(d("in_l_shadow.bin", np.float32)), L.hptr(d("in_l_scene.bin", np.float32)),
-                                           L.hptr(d("in_l_light.bin", np.float32))))
+        ctx.check(L.dll.rt_scene_set_bounds(scene, L.hptr(f32["bound"])))
+        ctx.check(L.dll.rt_scene_set_materials(scene, L.hptr(f32["materials"]), 2))
+        ctx.check(L.dll.rt_scene_add_set(scene, C.byref(gs), L.hptr(f32["sbound"]), 0, 0))
+        ctx.check(L.dll.rt_scene_add_set(scene, C.byref(gt), L.hptr(f32["tbound"]), 0, 0))
+        ctx.check(L.dll.rt_scene_add_light(scene, L.hptr(f32["l_shadow"]), L.hptr(f32["l_scene"]), L.hptr(f32["l_light"])))
         opts = L.RenderOpts()
         opts.cols, opts.rows, opts.rays_per_pixel, opts.depth = cols, rows, rpp, 5
         opts.focal_length, opts.lens_rad = 5.0, np.float32(0.05)
@@ -93,7 +93,7 @@ def test_addon_renders_like_the_ctypes_binding(rt, addon_test, tmp_path):
         ctx.check(L.dll.rt_render_create(ctx.h, scene, C.byref(opts), C.byref(render)))
         seeds = d("in_seeds.bin", np.int32)
         ctx.check(L.dll.rt_render_set_seeds(render, L.hptr(seeds), total, 0))
-        cam = d("in_cam.bin", np.float32)
+        cam = f32["cam"]
         pix = np.zeros(cols * rows * 4, np.uint8)
         for _ in range(2):
             ctx.check(L.dll.rt_render_execute(render, L.hptr(cam), L.hptr(pix)))
