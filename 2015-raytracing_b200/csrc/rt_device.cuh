@@ -134,6 +134,9 @@ RT_DEV void getRay(const Camera& cam, float col, float row, f3& o, f3& d) {
     o = cam.eye;
 }
 
+#ifndef RT_SINCOS
+#define RT_SINCOS 1
+#endif
 // A10/code.cl:143-172 (Shirley/Whittle concentric map).
 RT_DEV f2 concentric_distort(f2 in) {
     if (in.x == 0.0f && in.y == 0.0f) return in;
@@ -149,8 +152,15 @@ RT_DEV f2 concentric_distort(f2 in) {
         phi = 1.57079632679489661923f - (0.78539816339744830962f * (a / b));
     }
     f2 r;
+#if RT_SINCOS
+    double sn, cs;   // one range reduction for both; same values as cos() and sin() (tests/test_gpu_a10.py checks every float of the range)
+    sincos((double)phi, &sn, &cs);
+    r.x = (float)cs * radius;
+    r.y = (float)sn * radius;
+#else
     r.x = cl_cos(phi) * radius;
     r.y = cl_sin(phi) * radius;
+#endif
     return r;
 }
 
@@ -211,6 +221,40 @@ RT_DEV AabbHit interAABB(f3 o, f3 d, const AABB& box) {
     ttmin = (box.pmin.z - o.z) / d.z;
     ttmax = (box.pmax.z - o.z) / d.z;
     if (d.z < 0) { tmp = ttmin; ttmin = ttmax; ttmax = tmp; }
+    h.tmin = cl_max(ttmin, h.tmin);
+    h.tmax = cl_min(ttmax, h.tmax);
+    if (h.tmin > h.tmax) return h;
+    h.v = true;
+    return h;
+}
+
+// interAABB that also hands out the three far-plane quotients (the per-axis ttmax after the swap) for the 1-cell walk.
+struct AabbFar { float tmin, tmax, fx, fy, fz; bool v; };
+RT_DEV AabbFar interAABBFar(f3 o, f3 d, const AABB& box) {
+    AabbFar h;
+    h.tmin = 0.0f;
+    h.tmax = RT_INF;
+    h.fx = h.fy = h.fz = 0.0f;
+    h.v = false;
+    float ttmin, ttmax, tmp;
+    ttmin = (box.pmin.x - o.x) / d.x;
+    ttmax = (box.pmax.x - o.x) / d.x;
+    if (d.x < 0) { tmp = ttmin; ttmin = ttmax; ttmax = tmp; }
+    h.fx = ttmax;
+    h.tmin = cl_max(ttmin, h.tmin);
+    h.tmax = cl_min(ttmax, h.tmax);
+    if (h.tmin > h.tmax) return h;
+    ttmin = (box.pmin.y - o.y) / d.y;
+    ttmax = (box.pmax.y - o.y) / d.y;
+    if (d.y < 0) { tmp = ttmin; ttmin = ttmax; ttmax = tmp; }
+    h.fy = ttmax;
+    h.tmin = cl_max(ttmin, h.tmin);
+    h.tmax = cl_min(ttmax, h.tmax);
+    if (h.tmin > h.tmax) return h;
+    ttmin = (box.pmin.z - o.z) / d.z;
+    ttmax = (box.pmax.z - o.z) / d.z;
+    if (d.z < 0) { tmp = ttmin; ttmin = ttmax; ttmax = tmp; }
+    h.fz = ttmax;
     h.tmin = cl_max(ttmin, h.tmin);
     h.tmax = cl_min(ttmax, h.tmax);
     if (h.tmin > h.tmax) return h;
@@ -638,19 +682,27 @@ RT_DEV Hit gridWalk(f3 o, f3 d, float maxt_in, const GridView& g, const AabbHit&
 // t_next = (pmin + (d >= 0 ? 1 : 0) * delta - o) / d, delta = (pmax - pmin) / 1.0f, and after the cell the
 // first step always reaches slab == limit (A10/code.cl:770-785), so the loop body runs exactly once.
 // Triangles come in the precomputed form (face vector, p0, e1, e2 -- f_precomputeTriangles).
-template <int PRIM, bool ANY, bool STATS>
+RT_DEV void cellExit(const AabbHit&, bool, float&, float&, float&) {}
+RT_DEV void cellExit(const AabbFar& b, bool far_ok, float& tx, float& ty, float& tz) {
+    if (far_ok) { tx = b.fx; ty = b.fy; tz = b.fz; }
+}
+template <int PRIM, bool ANY, bool STATS, typename BI>
 RT_DEV Hit singleCellWalk(f3 o, f3 d, float maxt_in, const GridView& g, const float4* __restrict__ pre_ng, const float4* __restrict__ pre_pe,
-                          const AabbHit& binter, WalkStats* st) {
+                          const BI& binter, WalkStats* st, bool far_ok = false) {
     Hit h;
     h.t = maxt_in;
     h.i = 0xFFFFFFFFu;
     h.beta = 0.f; h.gamma = 0.f;
     h.cx = h.cy = h.cz = 1;
-    const float dx = (g.bound.pmax.x - g.bound.pmin.x) / 1.0f, dy = (g.bound.pmax.y - g.bound.pmin.y) / 1.0f,
-                dz = (g.bound.pmax.z - g.bound.pmin.z) / 1.0f;
-    const float tx = ((g.bound.pmin.x + (float)((d.x >= 0) ? 1 : 0) * dx) - o.x) / d.x;
-    const float ty = ((g.bound.pmin.y + (float)((d.y >= 0) ? 1 : 0) * dy) - o.y) / d.y;
-    const float tz = ((g.bound.pmin.z + (float)((d.z >= 0) ? 1 : 0) * dz) - o.z) / d.z;
+    float tx, ty, tz;
+    if (!far_ok) {
+        const float dx = (g.bound.pmax.x - g.bound.pmin.x) / 1.0f, dy = (g.bound.pmax.y - g.bound.pmin.y) / 1.0f,
+                    dz = (g.bound.pmax.z - g.bound.pmin.z) / 1.0f;
+        tx = ((g.bound.pmin.x + (float)((d.x >= 0) ? 1 : 0) * dx) - o.x) / d.x;
+        ty = ((g.bound.pmin.y + (float)((d.y >= 0) ? 1 : 0) * dy) - o.y) / d.y;
+        tz = ((g.bound.pmin.z + (float)((d.z >= 0) ? 1 : 0) * dz) - o.z) / d.z;
+    }
+    cellExit(binter, far_ok, tx, ty, tz);   // the box's own far-plane quotients when they are the same numbers (farPlanesShared)
     const float mint = binter.tmin;
     const float maxt = cl_min(cl_min(tx, ty), tz);
     const unsigned begin = __ldg(g.box), end = __ldg(g.box + 1);

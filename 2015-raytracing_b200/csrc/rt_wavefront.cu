@@ -30,6 +30,7 @@ struct SetDev {
     const float4* pre_pe;      // heavy triangle sets: (p0, e1, e2) per reference
     const unsigned* macro_occ; // heavy sets: coarse occupancy (<= 64^3 bits)
     unsigned macro_shift, macro_n;
+    int far_ok;                // 1-cell sets: the cell's exit planes are bit for bit the box's far planes (see farPlanesShared)
 };
 struct LightDev { LightArg shadow, scene, light; };
 struct SceneDev {
@@ -130,11 +131,11 @@ RT_DEV void flushProfile(unsigned* prof, unsigned long long* table, int set, int
 // sets are "heavy" and go to the queue walkers): only singleCellWalk is compiled in.
 RT_DEV void closestSet1(const SetDev& s, RayR& ray, PoiR& poi) {
     if (ray.mint == ray.maxt) return;
-    AabbHit binter = interAABB(ray.o, ray.d, s.g.bound);
+    AabbFar binter = interAABBFar(ray.o, ray.d, s.g.bound);
     if (!binter.v) return;
     Hit h;
-    if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, false, false>(ray.o, ray.d, ray.maxt, s.g, nullptr, nullptr, binter, nullptr);
-    else h = singleCellWalk<PRIM_TRIANGLE, false, false>(ray.o, ray.d, ray.maxt, s.g, s.pre_ng, s.pre_pe, binter, nullptr);
+    if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, false, false>(ray.o, ray.d, ray.maxt, s.g, nullptr, nullptr, binter, nullptr, s.far_ok);
+    else h = singleCellWalk<PRIM_TRIANGLE, false, false>(ray.o, ray.d, ray.maxt, s.g, s.pre_ng, s.pre_pe, binter, nullptr, s.far_ok);
     if (h.i == 0xFFFFFFFFu) return;
     ray.maxt = h.t;
     poi.p = getPoint(ray.o, ray.d, h.t);
@@ -150,11 +151,11 @@ RT_DEV void closestSet1(const SetDev& s, RayR& ray, PoiR& poi) {
 }
 RT_DEV void anySet1(const SetDev& s, RayR& sr) {
     if (sr.mint == sr.maxt) return;
-    AabbHit binter = interAABB(sr.o, sr.d, s.g.bound);
+    AabbFar binter = interAABBFar(sr.o, sr.d, s.g.bound);
     if (!binter.v) return;
     Hit h;
-    if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, true, false>(sr.o, sr.d, sr.maxt, s.g, nullptr, nullptr, binter, nullptr);
-    else h = singleCellWalk<PRIM_TRIANGLE, true, false>(sr.o, sr.d, sr.maxt, s.g, s.pre_ng, s.pre_pe, binter, nullptr);
+    if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, true, false>(sr.o, sr.d, sr.maxt, s.g, nullptr, nullptr, binter, nullptr, s.far_ok);
+    else h = singleCellWalk<PRIM_TRIANGLE, true, false>(sr.o, sr.d, sr.maxt, s.g, s.pre_ng, s.pre_pe, binter, nullptr, s.far_ok);
     if (h.i != 0xFFFFFFFFu) { sr.maxt = h.t; sr.mint = h.t; }
     else sr.maxt = h.t;
 }
@@ -279,6 +280,31 @@ __global__ void __launch_bounds__(128) k_pathMega(const __grid_constant__ SceneD
     }
 }
 
+// With n_slabs = 1 the DDA's first "next plane" of an axis is (pmin + (d >= 0 ? 1 : 0) * delta - o) / d with
+// delta = (pmax - pmin) / 1.0f (A10/code.cl:696-707).  That is bit for bit the far-plane quotient the slab test of
+// interAABB has just computed for the same box -- (pmax - o) / d for d >= 0, (pmin - o) / d for d < 0 (A10/code.cl:344-352)
+// -- when, in fp32, pmin + (pmax - pmin) == pmax exactly, the extent is finite, and pmin is not -0 (so that
+// pmin + 0 * delta keeps its bits).  Checked here, on the host, with the same fp32 operations; the stage kernels then
+// reuse the three quotients instead of dividing again (RT_FAR_SHARE).  Boxes that fail the check take the plain path.
+#ifndef RT_FAR_SHARE
+#define RT_FAR_SHARE 1
+#endif
+bool farPlanesShared(const float* b8) {
+    for (int a = 0; a < 3; a++) {
+        volatile float lo = b8[a], hi = b8[4 + a];
+        volatile float delta = (hi - lo) / 1.0f;
+        volatile float one = 1.0f * delta, zero = 0.0f * delta;
+        volatile float up = lo + one, down = lo + zero;
+        unsigned lo_bits, down_bits;
+        float lo_v = lo, down_v = down;
+        memcpy(&lo_bits, &lo_v, 4);
+        memcpy(&down_bits, &down_v, 4);
+        if (!(delta == delta) || delta > 3.0e38f || delta < -3.0e38f) return false;
+        if (!(up == hi) || lo_bits != down_bits) return false;
+    }
+    return true;
+}
+
 int buildSceneDev(rt_render* r, SceneDev& sc) {
     rt_scene* s = r->scene;
     if ((int)s->sets.size() > kMaxSets || (int)s->lights.size() > kMaxLights)
@@ -305,6 +331,7 @@ int buildSceneDev(rt_render* r, SceneDev& sc) {
         d.macro_occ = in.macro_occ;
         d.macro_shift = in.macro_shift;
         d.macro_n = in.macro_n;
+        d.far_ok = (RT_FAR_SHARE && in.grid.n_slabs == 1 && farPlanesShared(in.bound)) ? 1 : 0;
     }
     for (int i = 0; i < sc.n_lights; i++) {
         memcpy(sc.lights[i].shadow.v, s->lights[i].shadow, 64);
@@ -530,13 +557,14 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
         if (acu_loaded) a.acu[id] = acu;
     }
     if (op.push_set >= 0) pushTask(want_push, id, w.queue, w.qctr + 2 * op.qslot);
-    for (int d = 16; d > 0; d >>= 1) {
-        n_closest += __shfl_down_sync(0xffffffffu, n_closest, d);
-        n_any += __shfl_down_sync(0xffffffffu, n_any, d);
+    // ray counters: only a stage that generates rays of a kind can have counted any (one redux + one atomic per warp)
+    if (GEN != 0) {
+        const unsigned t = __reduce_add_sync(0xffffffffu, n_closest);
+        if ((threadIdx.x & 31) == 0 && t) atomicAdd(a.counters + 0, (unsigned long long)t);
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (n_closest) atomicAdd(a.counters + 0, (unsigned long long)n_closest);
-        if (n_any) atomicAdd(a.counters + 1, (unsigned long long)n_any);
+    if (SHADOW) {
+        const unsigned t = __reduce_add_sync(0xffffffffu, n_any);
+        if ((threadIdx.x & 31) == 0 && t) atomicAdd(a.counters + 1, (unsigned long long)t);
     }
 }
 

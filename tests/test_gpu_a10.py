@@ -422,3 +422,20 @@ def test_checkpoint_resume_is_bit_exact(rt, scenes, tmp_path):
     from PIL import Image
     back = np.asarray(Image.open(str(png)).convert("RGBA"))
     assert np.array_equal(back, img_a)
+
+
+def test_sincos_equals_separate_sin_and_cos(tmp_path):
+    """The concentric map's cos/sin pair comes from one sincos() call on the GPU (RT_SINCOS in rt_device.cuh); the arithmetic
+    contract says double-precision cos and sin rounded to fp32.  Exhaustive over every fp32 angle with |x| <= 4."""
+    import os
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available on this box")
+    exe = str(tmp_path / "sincos_check")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sincos_check.cu")
+    b = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-o", exe, src], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert b.returncode == 0, b.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout
