@@ -198,6 +198,13 @@ int tileReferenceSchedule(rt_render* r, const float* fcam, size_t slot0, unsigne
 
 }  // namespace
 
+int rt_seeds_ready(rt_render* r) {
+    if (!r->seeds_in_flight) return RT_OK;
+    RT_CUDA(r->ctx, cudaStreamWaitEvent(r->ctx->stream, r->ev_seeds, 0));
+    r->seeds_in_flight = false;
+    return RT_OK;
+}
+
 int rt_time_mark(rt_render* r, int cls) {
     if (!r->timing) return RT_OK;
     rt_ctx* ctx = r->ctx;
@@ -352,6 +359,9 @@ int rt_render_destroy(rt_render* r) {
     void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rays, r->pois, r->shadow, r->d_counters, r->d_profile,
                     r->w_ray, r->w_poi, r->w_atte, r->w_sh, r->w_queue, r->w_qctr};
     for (void* b : bufs) if (b) cudaFree(b);
+    if (r->copy_stream) { cudaStreamSynchronize(r->copy_stream); cudaStreamDestroy(r->copy_stream); }
+    if (r->ev_seeds) cudaEventDestroy(r->ev_seeds);
+    if (r->ev_main) cudaEventDestroy(r->ev_main);
     if (r->ev0) cudaEventDestroy(r->ev0);
     if (r->ev1) cudaEventDestroy(r->ev1);
     for (cudaEvent_t e : r->tev) cudaEventDestroy(e);
@@ -377,6 +387,7 @@ int rt_render_set_seeds(rt_render* r, const int* seeds, size_t count, int on_dev
     size_t total = r->pixels * o.rays_per_pixel;
     if (count != total) return rt_fail(ctx, RT_ERR_INVALID, "set_seeds: count must be cols*rows*rays_per_pixel");
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_TRY(rt_seeds_ready(r));
     if (r->slots_pp == o.rays_per_pixel) {
         RT_CUDA(ctx, cudaMemcpyAsync(r->seeds, seeds, sizeof(int) * total, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     } else if (on_device) {
@@ -397,8 +408,32 @@ int rt_render_write_local_seeds(rt_render* r, const int* host_seeds, size_t coun
     rt_ctx* ctx = r->ctx;
     if (count != r->local_slots) return rt_fail(ctx, RT_ERR_INVALID, "write_local_seeds: count must be cols*rows*slot_count");
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_TRY(rt_seeds_ready(r));
     RT_CUDA(ctx, cudaMemcpyAsync(r->seeds, host_seeds, sizeof(int) * count, cudaMemcpyHostToDevice, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    r->have_seeds = true;
+    return RT_OK;
+}
+
+// Non-blocking form (the reference's own uploads are enqueueWriteBuffer(buf, false, ...), A10/code.js:1149): the copy
+// is issued on a side stream behind everything already queued on the context's stream and returns at once; the
+// next pass starts immediately and waits for it only in front of its first kernel that reads seeds -- with
+// rays_per_pixel > 1 that is the first shadow-ray stage, so the upload overlaps ray generation and the primary traversal.
+int rt_render_write_local_seeds_async(rt_render* r, const int* host_seeds, size_t count) {
+    if (!r || !host_seeds) return RT_ERR_INVALID;
+    rt_ctx* ctx = r->ctx;
+    if (count != r->local_slots) return rt_fail(ctx, RT_ERR_INVALID, "write_local_seeds_async: count must be cols*rows*slot_count");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!r->copy_stream) {
+        RT_CUDA(ctx, cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&r->ev_seeds, cudaEventDisableTiming));
+        RT_CUDA(ctx, cudaEventCreateWithFlags(&r->ev_main, cudaEventDisableTiming));
+    }
+    RT_CUDA(ctx, cudaEventRecord(r->ev_main, ctx->stream));             // after the passes that still read / write the old seeds
+    RT_CUDA(ctx, cudaStreamWaitEvent(r->copy_stream, r->ev_main, 0));
+    RT_CUDA(ctx, cudaMemcpyAsync(r->seeds, host_seeds, sizeof(int) * count, cudaMemcpyHostToDevice, r->copy_stream));
+    RT_CUDA(ctx, cudaEventRecord(r->ev_seeds, r->copy_stream));
+    r->seeds_in_flight = true;
     r->have_seeds = true;
     return RT_OK;
 }
@@ -453,6 +488,9 @@ int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pi
     RT_CUDA(ctx, cudaEventRecord(r->ev0, ctx->stream));
     r->tev_used = 0;
     float2* coords = nullptr;
+    // the wavefront path of a stratified pass (rays_per_pixel > 1) first needs seeds at its first shadow stage and waits
+    // there (rt_wavefront.cu); every other path reads them from its first kernel on
+    if (o.rays_per_pixel == 1 || o.mode != 0 || r->profile) RT_TRY(rt_seeds_ready(r));
     if (o.rays_per_pixel == 1) {
         RT_CUDA(ctx, cudaMallocAsync((void**)&coords, sizeof(float2) * r->pixels, ctx->stream));
         f_rpp1_coords<<<rt_blocks(o.cols, 64), 64, 0, ctx->stream>>>(r->seeds, coords, o.cols, o.rows);
@@ -509,11 +547,13 @@ int rt_render_read_accum(rt_render* r, float* host_float4) {
 int rt_render_read_seeds(rt_render* r, int* host_seeds, size_t count) {
     if (!r || !host_seeds) return RT_ERR_INVALID;
     if (count != r->local_slots) return rt_fail(r->ctx, RT_ERR_INVALID, "read_seeds: count must be cols*rows*slot_count");
+    RT_TRY(rt_seeds_ready(r));
     return rt_buffer_read(r->ctx, r->seeds, 0, sizeof(int) * count, host_seeds);
 }
 
 int rt_render_export_state(rt_render* r, float* host_acu, int* host_seeds, unsigned* passes) {
     if (!r) return RT_ERR_INVALID;
+    RT_TRY(rt_seeds_ready(r));
     if (host_acu) RT_TRY(rt_buffer_read(r->ctx, r->acu, 0, sizeof(float4) * r->local_slots, host_acu));
     if (host_seeds) RT_TRY(rt_buffer_read(r->ctx, r->seeds, 0, sizeof(int) * r->local_slots, host_seeds));
     if (passes) *passes = r->passes;
@@ -522,6 +562,7 @@ int rt_render_export_state(rt_render* r, float* host_acu, int* host_seeds, unsig
 
 int rt_render_import_state(rt_render* r, const float* host_acu, const int* host_seeds, unsigned passes) {
     if (!r || passes == 0) return RT_ERR_INVALID;
+    RT_TRY(rt_seeds_ready(r));
     if (host_acu) RT_TRY(rt_buffer_write(r->ctx, r->acu, 0, sizeof(float4) * r->local_slots, host_acu));
     if (host_seeds) {
         RT_TRY(rt_buffer_write(r->ctx, r->seeds, 0, sizeof(int) * r->local_slots, host_seeds));

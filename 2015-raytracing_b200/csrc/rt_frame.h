@@ -43,6 +43,11 @@ struct rt_render {
     float4* accum = nullptr;         // [pixel] sum over k_local
     uchar4* pixel = nullptr;
     bool have_seeds = false;
+    // non-blocking seed upload (rt_render_write_local_seeds_async): side stream + the event the pass waits on
+    // right before its first seed-consuming kernel
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_seeds = nullptr, ev_main = nullptr;
+    bool seeds_in_flight = false;
     unsigned passes = 1;             // the reference starts at 1 and divides by it (A10/code.js:416,1850)
     // per tile
     rt::Ray* rays = nullptr;
@@ -72,6 +77,10 @@ struct rt_render {
     float class_ms[RT_TIMING_CLASSES] = {0};
     unsigned class_launches[RT_TIMING_CLASSES] = {0};
 };
+
+// Orders the context's stream after a seed upload that is still in flight (no-op otherwise).  Called in front of
+// the first kernel of a pass that reads the seed buffer, and by everything else that touches it.
+int rt_seeds_ready(rt_render* r);
 
 // Marks the start of a launch of timing class `cls` (no-op unless timing is on).
 int rt_time_mark(rt_render* r, int cls);

@@ -1269,6 +1269,7 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
     std::vector<Stage> stages;
     rc = buildStages(r, stages);
     if (rc) {   // more walk stages than queue counters: run the tile through the megakernel instead
+        RT_TRY_W(rt_seeds_ready(r));
         RT_TRY_W(rt_time_mark(r, 5));
         k_pathMega<false><<<rt_blocks(a.n_local, 128), 128, 0, ctx->stream>>>(sc, a);
         RT_LAUNCH_CHECK(ctx, "pathMega");
@@ -1279,6 +1280,10 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
     const unsigned n = a.n_local;
     for (const Stage& s : stages) {
         if (!s.is_walk) {
+            // a seed upload still in flight (rt_render_write_local_seeds_async) is waited for here, in front of the
+            // first stage that draws random numbers: bouncePaths / initShadowTrace (initTrace only when rpp == 1,
+            // and then rt_render_execute has waited already)
+            if (s.op.gen == 2 || s.op.shadow_light >= 0) RT_TRY_W(rt_seeds_ready(r));
             RT_TRY_W(rt_time_mark(r, 0));
             launchStage(ctx, sc, a, w, s.op, n);
             RT_LAUNCH_CHECK(ctx, "wave_stage");
@@ -1349,6 +1354,7 @@ int rt_fused_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, con
     bool any_heavy = false;
     for (const SceneSet& s : r->scene->sets) any_heavy = any_heavy || isHeavy(s);
     if (o.mode == 2 || !any_heavy) {   // megakernel: explicit, or nothing would be queued anyway
+        RT_TRY_W(rt_seeds_ready(r));
         RT_TRY_W(rt_time_mark(r, 5));
         k_pathMega<false><<<rt_blocks(n, 128), 128, 0, ctx->stream>>>(sc, a);
         RT_LAUNCH_CHECK(ctx, "pathMega");

@@ -725,11 +725,23 @@ class Renderer:
         seeds = np.ascontiguousarray(seeds, dtype=np.int32)
         self.ctx.check(L.dll.rt_render_set_seeds(self.h_render, seeds.ctypes.data, seeds.size, 0))
 
+    def writeLocalSeeds(self, seeds, non_blocking=False):
+        """Upload THIS renderer's seeds, laid out [pixel][k_local] (= the global layout when it renders every slot).
+        ``non_blocking=True`` is the reference's enqueueWriteBuffer(buf, false, ...): the copy overlaps the head of the next
+        executeRender (rt_render_write_local_seeds_async); the array is kept alive until that pass has returned."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.int32)
+        if non_blocking:
+            self._seed_keepalive = seeds
+            self.ctx.check(L.dll.rt_render_write_local_seeds_async(self.h_render, seeds.ctypes.data, seeds.size))
+        else:
+            self.ctx.check(L.dll.rt_render_write_local_seeds(self.h_render, seeds.ctypes.data, seeds.size))
+
     # -- executeRender: A10/code.js:1806-1854 (one pass, returns the RGBA image) --
     def executeRender(self, camera=None, readback=True):
         cam = (camera or self.scene["camera"]).toFloat32Array()
         img = np.empty((self.height, self.width, 4), dtype=np.uint8) if readback else None
         self.ctx.check(L.dll.rt_render_execute(self.h_render, L.hptr(cam), L.hptr(img)))
+        self._seed_keepalive = None
         self.passes += 1
         return img
 

@@ -139,6 +139,7 @@ _SIGS = {
     "rt_render_read_accum": ([P, P], I),
     "rt_render_read_seeds": ([P, P, Z], I),
     "rt_render_write_local_seeds": ([P, P, Z], I),
+    "rt_render_write_local_seeds_async": ([P, P, Z], I),
     "rt_render_export_state": ([P, P, P, C.POINTER(U)], I),
     "rt_render_import_state": ([P, P, P, U], I),
     "rt_render_set_profile": ([P, I], I),

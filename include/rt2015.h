@@ -271,6 +271,11 @@ int rt_render_read_seeds(rt_render*, int* host_seeds, size_t count);            
 /* Same as rt_render_set_seeds for a caller that already holds only THIS context's slots, laid out
  * [pixel][k_local] (count = cols*rows*slot_count host ints). */
 int rt_render_write_local_seeds(rt_render*, const int* host_seeds, size_t count);
+/* Non-blocking form of the same upload, like the reference's own enqueueWriteBuffer(buf, false, ...) (A10/code.js:1149):
+ * issued on a side stream behind the work already queued, returns at once; the next rt_render_execute overlaps it with
+ * ray generation and the primary traversal and waits for it in front of its first kernel that draws random numbers.
+ * `host_seeds` (pinned memory for a truly asynchronous copy) must stay valid until that rt_render_execute has returned. */
+int rt_render_write_local_seeds_async(rt_render*, const int* host_seeds, size_t count);
 /* Progressive state of a render = what lives only on the device between passes in the reference: the per-slot
  * accumulators, the per-slot seeds and the pass counter (A10/code.js:416, 1078-1099, 1140-1154, 1853).  Export after
  * any pass, import into a render created with the same scene/options to resume bit-exactly where it stopped

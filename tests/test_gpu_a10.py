@@ -439,3 +439,31 @@ def test_sincos_equals_separate_sin_and_cos(tmp_path):
     assert b.returncode == 0, b.stdout
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout
+
+
+@pytest.mark.parametrize("mode,rpp", [(0, 4), (0, 1), (2, 4), (1, 4)])
+def test_non_blocking_seed_upload_is_equivalent(rt, scenes, mode, rpp):
+    """rt_render_write_local_seeds_async (the reference's non-blocking enqueueWriteBuffer) overlaps the upload with the head of the
+    next pass; whichever kernel reads the seeds first must see them: every path (wavefront, rpp == 1, megakernel, reference
+    schedule) gives the results of the blocking upload, pass after pass, also when the seeds are replaced between passes."""
+    import torch
+    _, p_scene = scenes
+    total = COLS * ROWS * rpp
+    seeds = [OR.make_seeds(total, 100 + k) for k in range(3)]
+    pinned = [torch.from_numpy(s.copy()).pin_memory() for s in seeds]
+    out = []
+    for non_blocking in (False, True):
+        r = rt.Renderer(p_scene, COLS, ROWS, rpp, mode=mode)
+        r.preRender(seeds[0])
+        res = []
+        try:
+            for k in range(3):
+                src = pinned[k].numpy() if non_blocking else seeds[k]
+                r.writeLocalSeeds(src, non_blocking=non_blocking)
+                pix = r.executeRender()
+                res.append((pix.copy(), r.accum(), r.seeds()))
+        finally:
+            r.postRender()
+        out.append(res)
+    for (p0, a0, s0), (p1, a1, s1) in zip(*out):
+        assert np.array_equal(s0, s1) and np.array_equal(a0.view(np.uint32), a1.view(np.uint32)) and np.array_equal(p0, p1)
