@@ -202,13 +202,13 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the walker kernels from the committed `ncu --set full`
-# capture of this command at N = 1 (profiles/r1c_walk_full_summary.md, mean over the captured launches).  A launch
+# capture of this command at N = 1 (profiles/r1d_walk_full_summary.md, mean over the captured launches).  A launch
 # walks the queue of ONE tile of ONE pipeline stage; at N = 1 the frame is two tiles (412 721 664 + 118 119 936 slots =
 # a quarter of device memory + the rest) and the captured launches belong to the SMALL tile, so the figure is per
 # 118 119 936 slots.  Traffic follows the number of queued rays, hence the slots: a step's total is the figure x
 # (slots of this rank / 118 119 936) x stages (any hit: (1 + depth) x lights, closest hit: 1 + depth), divided over
 # the launches of the step for the per-launch average reported next to `achieved`.  Default workload only.
-NCU_TRAFFIC = {"walk_triangle_any": 22476466064, "walk_triangle_closest": 22222815120}
+NCU_TRAFFIC = {"walk_triangle_any": 22458861576, "walk_triangle_closest": 22251870372}
 NCU_TRAFFIC_SLOTS = 118119936
 NCU_TRAFFIC_WORKLOAD = (1920, 1080, 256, 1000, 500, 128, 2)
 
