@@ -381,6 +381,8 @@ def main():
                     "d2h_bytes_per_step": int(args.cols * args.rows * 4), "ms_per_step": round(ms_e / args.steps, 3)},
             "gpu_launches": int(launches),
             "rays_per_step": int(rays // max(args.steps, 1)),
+            # the reference launches every kernel over EVERY slot, alive or not: slot passes per second for comparison
+            "slot_passes_per_s": round(args.cols * args.rows * args.spp / (ms / args.steps * 1e-3), 0),
             "roofline": roofline,
             "cpu_baseline": cpu,
         }

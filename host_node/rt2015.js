@@ -365,8 +365,15 @@ class Renderer {
     return s;
   }
   setSeeds(seeds) { rt.render_set_seeds(this.hRender, seeds, seeds.length, 0); }
+  // this renderer's own slots, [pixel][k_local]; nonBlocking = enqueueWriteBuffer(buf, false, ...): the copy overlaps the
+  // head of the next executeRender, which keeps `seeds` alive until it has returned
+  writeLocalSeeds(seeds, nonBlocking) {
+    if (nonBlocking) { this._seedKeepAlive = seeds; rt.render_write_local_seeds_async(this.hRender, seeds, seeds.length); }
+    else rt.render_write_local_seeds(this.hRender, seeds, seeds.length);
+  }
   executeRender(camera) {   // + sendImagetoHTML (:1530-1537): this.image receives copyToPixel's RGBA
     rt.render_execute(this.hRender, (camera || this.scene.camera).toFloat32Array(), this.image);
+    this._seedKeepAlive = null;
     this.passes++;
     return this.image;
   }
