@@ -99,3 +99,32 @@ def test_random_scene_matches_oracle(rt, oracle_lib, tmp_path, case, mode):
             assert (closest, anyh) == (st.n_closest, st.n_any), "case %d pass %d: valid-ray counts differ" % (case, p)
     finally:
         r.postRender()
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_random_scene_a08_a09_match_oracle(rt, gpu_ctx, ref_lib, tmp_path, case):
+    """The same random scenes through the deterministic frames of Assignments 8 and 9 (point lights, shadow rays, thin
+    lens; launcher by launcher like their render()), n_slabs 1 / 3 / 5: hit ids, hit distances, float image and pixels."""
+    rng = np.random.Generator(np.random.PCG64(8000 + case))
+    d = tmp_path / "scenes"
+    d.mkdir()
+    path = str(d / "random.xml")
+    with open(path, "w", encoding="utf-8") as f:
+        f.write(random_scene_xml(rng, False))
+    n_slabs = (1, 3, 5)[case % 3]
+    for a in (8, 9):
+        o_scene, p_scene = OH.loadScene(path, COLS, ROWS, assignment=a), rt.loadScene(path, COLS, ROWS, assignment=a)
+        if not (len(o_scene["spheres"]) or len(o_scene["triangles"])):
+            continue
+        if a == 8:
+            acu_o, pix_o, st = OR.a08_render(ref_lib, o_scene, COLS, ROWS, n_slabs)
+            acu, pix, matid, maxt = rt.assignments.a08_render(gpu_ctx, p_scene, COLS, ROWS, n_slabs)
+        else:
+            acu_o, pix_o, st = OR.a09_render(ref_lib, o_scene, COLS, ROWS, 4, n_slabs)
+            acu, pix, matid, maxt = rt.assignments.a09_render(gpu_ctx, p_scene, COLS, ROWS, 4, n_slabs)
+        want_id = st["pois"]["matId"].astype(np.int32)
+        assert np.array_equal(matid, want_id), "A%02d case %d: hit ids" % (a, case)
+        hit = want_id >= 0
+        assert np.array_equal(maxt[hit].view(np.uint32), st["rays"]["maxt"][hit].view(np.uint32)), "A%02d case %d: hit distances" % (a, case)
+        assert np.array_equal(acu.view(np.uint32), np.ascontiguousarray(acu_o, dtype=np.float32).view(np.uint32)), "A%02d case %d: float image" % (a, case)
+        assert np.array_equal(pix.reshape(-1, 4), np.asarray(pix_o).reshape(-1, 4)), "A%02d case %d: pixels" % (a, case)
