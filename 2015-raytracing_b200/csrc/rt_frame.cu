@@ -333,6 +333,9 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     A((void**)&r->acu, sizeof(float4) * r->local_slots);
     A((void**)&r->accum, sizeof(float4) * r->pixels);
     A((void**)&r->pixel, sizeof(uchar4) * r->pixels);
+    // kept for the life of the render: a per-pass cudaMallocAsync of this buffer cost ~27 ms a pass at 1080p (the
+    // stream-ordered pool hands its memory back at every synchronisation) -- three times the pass's kernels
+    if (r->o.rays_per_pixel == 1) A((void**)&r->rpp1_coords, sizeof(float2) * r->pixels);
     if (r->o.mode == 1) {   // the kernel-by-kernel schedule keeps the reference's AoS state per tile
         A((void**)&r->rays, sizeof(Ray) * r->tile_slots);
         A((void**)&r->pois, sizeof(Poi10) * r->tile_slots);
@@ -356,7 +359,7 @@ int rt_render_destroy(rt_render* r) {
     rt_ctx* ctx = r->ctx;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rays, r->pois, r->shadow, r->d_counters, r->d_profile,
+    void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rpp1_coords, r->rays, r->pois, r->shadow, r->d_counters, r->d_profile,
                     r->w_ray, r->w_poi, r->w_atte, r->w_sh, r->w_queue, r->w_qctr};
     for (void* b : bufs) if (b) cudaFree(b);
     if (r->copy_stream) { cudaStreamSynchronize(r->copy_stream); cudaStreamDestroy(r->copy_stream); }
@@ -492,7 +495,7 @@ int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pi
     // there (rt_wavefront.cu); every other path reads them from its first kernel on
     if (o.rays_per_pixel == 1 || o.mode != 0 || r->profile) RT_TRY(rt_seeds_ready(r));
     if (o.rays_per_pixel == 1) {
-        RT_CUDA(ctx, cudaMallocAsync((void**)&coords, sizeof(float2) * r->pixels, ctx->stream));
+        coords = r->rpp1_coords;
         f_rpp1_coords<<<rt_blocks(o.cols, 64), 64, 0, ctx->stream>>>(r->seeds, coords, o.cols, o.rows);
         RT_LAUNCH_CHECK(ctx, "initTrace(seeds)");
     }
@@ -504,7 +507,6 @@ int rt_render_execute(rt_render* r, const float fcam[16], unsigned char* host_pi
         else rc = rt_fused_tile(r, fcam, slot0, n, coords);
         if (rc) return rc;
     }
-    if (coords) RT_CUDA(ctx, cudaFreeAsync(coords, ctx->stream));
     RT_TRY(rt_time_mark(r, 7));
     f_sumSlots<<<rt_blocks(r->pixels, kBlock), kBlock, 0, ctx->stream>>>(r->acu, r->accum, r->pixels, r->slots_pp);
     RT_LAUNCH_CHECK(ctx, "sumSlots");

@@ -42,6 +42,7 @@ struct rt_render {
     float4* acu = nullptr;           // [pixel][k_local]
     float4* accum = nullptr;         // [pixel] sum over k_local
     uchar4* pixel = nullptr;
+    float2* rpp1_coords = nullptr;   // rays_per_pixel == 1 only: the lens coordinates initTrace draws, [pixel] (quirk Q7)
     bool have_seeds = false;
     // non-blocking seed upload (rt_render_write_local_seeds_async): side stream + the event the pass waits on
     // right before its first seed-consuming kernel
