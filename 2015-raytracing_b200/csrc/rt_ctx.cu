@@ -21,6 +21,19 @@ int rt_ctx_create(int device_ordinal, rt_ctx** out) {
         delete ctx;
         return RT_ERR_CUDA;
     }
+    cudaMemPoolProps pp;
+    memset(&pp, 0, sizeof pp);
+    pp.allocType = cudaMemAllocationTypePinned;
+    pp.handleTypes = cudaMemHandleTypeNone;
+    pp.location.type = cudaMemLocationTypeDevice;
+    pp.location.id = ctx->device;
+    if (cudaMemPoolCreate(&ctx->pool, &pp) == cudaSuccess) {
+        unsigned long long keep = ~0ull;   // never trim at synchronisation points
+        cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    } else {
+        ctx->pool = nullptr;               // fall back to the device's default pool
+        cudaGetLastError();
+    }
     *out = ctx;
     return RT_OK;
 }
@@ -29,6 +42,7 @@ int rt_ctx_destroy(rt_ctx* ctx) {
     RT_CHECK_CTX(ctx);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RT_OK;

@@ -136,7 +136,7 @@ int exclusiveScan(rt_ctx* ctx, const unsigned* in, unsigned* out, size_t n) {
     if (n == 0) return RT_OK;
     size_t tiles = (n + kScanTile - 1) / kScanTile;
     unsigned* sums = nullptr;
-    RT_CUDA(ctx, cudaMallocAsync((void**)&sums, sizeof(unsigned) * tiles, ctx->stream));
+    RT_CUDA(ctx, rt_scratch_alloc(ctx, (void**)&sums, sizeof(unsigned) * tiles));
     k_scan_tiles<<<(unsigned)tiles, kScanBlock, 0, ctx->stream>>>(in, out, sums, n);
     RT_LAUNCH_CHECK(ctx, "scan_tiles");
     if (tiles > 1) {
@@ -305,7 +305,7 @@ struct Scratch {   // frees everything it owns (stream-ordered) on scope exit
     }
     template <typename T>
     cudaError_t alloc(T** p, size_t count) {
-        cudaError_t e = cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), ctx->stream);
+        cudaError_t e = rt_scratch_alloc(ctx, (void**)p, sizeof(T) * (count ? count : 1));
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }

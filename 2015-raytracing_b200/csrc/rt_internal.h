@@ -19,7 +19,15 @@ struct rt_ctx {
     unsigned* st_cells = nullptr;
     unsigned* st_tests = nullptr;
     unsigned long long launches = 0;   // kernels launched through this context
+    // scratch allocations (grid build, rpp == 1 launcher) come from a pool of the context's own that KEEPS its memory
+    // between calls: the device's default pool releases everything at each synchronisation, which made a per-pass
+    // 16 MB cudaMallocAsync cost 27 ms
+    cudaMemPool_t pool = nullptr;
 };
+
+static inline cudaError_t rt_scratch_alloc(rt_ctx* ctx, void** p, size_t bytes) {
+    return ctx->pool ? cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
+}
 
 #define RT_CHECK_CTX(ctx)              \
     do {                               \

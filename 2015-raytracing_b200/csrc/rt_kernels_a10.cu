@@ -335,7 +335,7 @@ int rt_a10_initTrace(rt_ctx* ctx, void* seeds, void* rays, void* pois, const flo
     } else {
         if (!seeds) return RT_ERR_INVALID;
         float2* coords = nullptr;
-        RT_CUDA(ctx, cudaMallocAsync((void**)&coords, sizeof(float2) * (size_t)total, ctx->stream));
+        RT_CUDA(ctx, rt_scratch_alloc(ctx, (void**)&coords, sizeof(float2) * (size_t)total));
         k_initTrace_rpp1_coords<<<rt_blocks(cols, 64), 64, 0, ctx->stream>>>((int*)seeds, coords, cols, rows);
         RT_LAUNCH_CHECK(ctx, "initTrace(seeds)");
         k_initTrace_rpp1<<<rt_blocks(total, kBlock), kBlock, 0, ctx->stream>>>(coords, (Ray*)rays, (Poi10*)pois, mkAabb(bound), mkCam(fcam),
