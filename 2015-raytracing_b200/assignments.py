@@ -401,6 +401,54 @@ def a09_render(ctx, scene, cols, rows, rays_per_pixel, n_slabs=5, focal_length=N
     return _ret(f, *out)
 
 
+def a089_render_fused(ctx, scene, cols, rows, assignment, rays_per_pixel=1, n_slabs=5, focal_length=None, lens_diameter=None, timing=False):
+    """render() of Assignment 8 (``assignment=8``: pinhole, one ray per pixel) or 9 (thin lens, ``rays_per_pixel`` a perfect square)
+    through rt_a089_render_frame: the whole launcher sequence of :func:`a08_render` / :func:`a09_render` in one kernel plus
+    copyToPixel.  Same return values, bit for bit."""
+    rpp = 1 if assignment == 8 else int(rays_per_pixel)
+    total = cols * rows * rpp
+    f = _Frame(ctx, timing)
+    grids = []
+    try:
+        S, T = _a089_sets(ctx, f, scene, n_slabs, grids)
+        d_acu, d_mat, d_pix = f.alloc(16 * total), f.upload(H.splitMaterialData(scene)), f.alloc(4 * cols * rows)
+        d_id, d_maxt = f.alloc(4 * total), f.alloc(4 * total)
+        lights = np.concatenate([_light_pos(v) for v in scene["lights"]]) if scene["lights"] else np.zeros(4, np.float32)
+        fr = L.A089Frame()
+        if S:
+            fr.spheres, fr.s_matid, fr.s_box_size, fr.s_n_slabs = S[0].prim, S[0].matid, S[0].box_size, int(n_slabs)
+            fr.s_bound[:] = [float(v) for v in S[1]]
+        if T:
+            fr.t_pos, fr.t_normal, fr.t_matid, fr.t_box_size, fr.t_n_slabs = T[0].prim, T[0].normal, T[0].matid, T[0].box_size, int(n_slabs)
+            fr.t_bound[:] = [float(v) for v in T[1]]
+            shadow_bb = H.bounds2AABB(scene["sphereBounds"]) if assignment == 8 else T[1]   # quirk Q10
+            fr.t_shadow_bound[:] = [float(v) for v in shadow_bb]
+        fr.material = d_mat
+        fr.light_pos, fr.n_lights = L.hptr(lights), len(scene["lights"])
+        fr.bound[:] = [float(v) for v in H.bounds2AABB(scene["bounds"])]
+        fr.fcam[:] = [float(v) for v in scene["camera"].toFloat32Array()]
+        if assignment != 8:
+            fl = scene["focal_length"] if focal_length is None else focal_length
+            ld = scene["lens_diameter"] if lens_diameter is None else lens_diameter
+            fr.focal_length, fr.lens_rad, fr.thin_lens = float(np.float32(fl)), float(np.float32(ld / 2.0)), 1
+        fr.rays_per_pixel = rpp
+        f.begin()
+        ctx.check(L.dll.rt_a089_render_frame(ctx.h, C.byref(fr), d_acu, d_id, d_maxt))
+        if assignment == 8:
+            ctx.call("rt_a08_copyToPixel", d_pix, d_acu, float(np.float32(1.0 / len(scene["lights"]))), cols * rows)
+        else:
+            ctx.call("rt_a09_copyToPixel", d_pix, d_acu, float(np.float32(1.0 / (rpp * len(scene["lights"])))), cols * rows, rpp)
+        f.end()
+        acu = ctx.download(d_acu, np.float32, 4 * total).reshape(-1, 4)
+        pix = ctx.download(d_pix, np.uint8, 4 * cols * rows).reshape(rows, cols, 4)
+        out = (acu, pix, ctx.download(d_id, np.int32, total), ctx.download(d_maxt, np.float32, total))
+    finally:
+        for g in grids:
+            L.dll.rt_grid_release(ctx.h, C.byref(g))
+        f.close()
+    return _ret(f, *out)
+
+
 def _a089_readback(ctx, d_acu, d_pix, d_pois, d_rays, total, cols, rows):
     acu = ctx.download(d_acu, np.float32, 4 * total).reshape(-1, 4)
     pix = ctx.download(d_pix, np.uint8, 4 * cols * rows).reshape(rows, cols, 4)

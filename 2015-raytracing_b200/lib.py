@@ -51,6 +51,14 @@ class MolData(C.Structure):
                 ("bounds_max", C.c_double * 3)]
 
 
+class A089Frame(C.Structure):
+    """rt_a089_frame."""
+    _fields_ = [("spheres", P), ("s_matid", P), ("s_box_size", P), ("s_bound", F * 8), ("s_n_slabs", U),
+                ("t_pos", P), ("t_normal", P), ("t_matid", P), ("t_box_size", P), ("t_bound", F * 8), ("t_n_slabs", U),
+                ("t_shadow_bound", F * 8), ("material", P), ("light_pos", P), ("n_lights", U), ("bound", F * 8), ("fcam", F * 16),
+                ("focal_length", F), ("lens_rad", F), ("rays_per_pixel", U), ("thin_lens", U)]
+
+
 class RenderOpts(C.Structure):
     """rt_render_opts."""
     _fields_ = [("cols", U), ("rows", U), ("rays_per_pixel", U), ("depth", U), ("focal_length", F), ("lens_rad", F),
@@ -116,6 +124,7 @@ _SIGS = {
     "rt_a09_triangleShadowTrace": ([P, U, P, P, P, P, U], I),
     "rt_a09_sceneRender": ([P, P, P, P, P, U], I),
     "rt_a09_copyToPixel": ([P, P, P, F, U, U], I),
+    "rt_a089_render_frame": ([P, C.POINTER(A089Frame), P, P, P], I),
     "rt_parse_mesh_json": ([C.c_char_p, Z, C.POINTER(MeshData)], I),
     "rt_mesh_data_free": ([C.POINTER(MeshData)], None),
     "rt_parse_pdb": ([C.c_char_p, Z, C.POINTER(MolData)], I),

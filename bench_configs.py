@@ -132,11 +132,15 @@ def main():
     g = best_gpu(lambda: A.a08_render(ctx, sc8_p, W, H, 5, timing=True), args.reps)
     c = cpu_time(lambda: OR.a08_render(olib, sc8_o, cw, ch, 5))
     emit("4a: A08 render (2 point lights), %dx%d, rpp 1" % (W, H), W * H, g, cw * ch, c)
+    g = best_gpu(lambda: A.a089_render_fused(ctx, sc8_p, W, H, 8, 1, 5, timing=True), args.reps)
+    emit("4a: A08 frame in one launch (rt_a089_render_frame), %dx%d, rpp 1" % (W, H), W * H, g, cw * ch, c)
     rpp = 16 if args.quick else 100
     sc9_p, sc9_o = rt.loadScene(path, W, H, assignment=9), OH.loadScene(path, cw, ch, assignment=9)
     g = best_gpu(lambda: A.a09_render(ctx, sc9_p, W, H, rpp, 5, timing=True), max(1, args.reps - 1))
     c = cpu_time(lambda: OR.a09_render(olib, sc9_o, cw, ch, 4, 5), 1)
     emit("4b: A09 render (thin lens), %dx%d, rpp %d (CPU: rpp 4)" % (W, H, rpp), W * H * rpp, g, cw * ch * 4, c)
+    g = best_gpu(lambda: A.a089_render_fused(ctx, sc9_p, W, H, 9, rpp, 5, timing=True), max(1, args.reps - 1))
+    emit("4b: A09 frame in one launch (rt_a089_render_frame), %dx%d, rpp %d (CPU: rpp 4)" % (W, H, rpp), W * H * rpp, g, cw * ch * 4, c)
     ctx.close()
     if args.out:
         with open(args.out, "w") as f:

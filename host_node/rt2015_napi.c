@@ -424,6 +424,54 @@ static napi_value js_render_stats(napi_env env, napi_callback_info info) {   /* 
     return o;
 }
 
+/* a089_render_frame(ctx, frame, acu, out_matid|null, out_maxt|null): the whole Assignment 8 / 9 frame in one launch.
+ * frame = { spheres: grid|null, s_bound: Float32Array(8), triangles: grid|null, t_bound, t_shadow_bound: Float32Array(8),
+ *           material: BigInt, light_pos: Float32Array(4 * n_lights), n_lights, bound: Float32Array(8), fcam: Float32Array(16),
+ *           focal_length, lens_rad, rays_per_pixel, thin_lens }  (grids as returned by grid_build_*) */
+static int copy_floats(napi_env env, napi_value obj, const char* key, float* dst, size_t n) {
+    napi_value v;
+    size_t bytes = 0;
+    if (napi_get_named_property(env, obj, key, &v) != napi_ok) return 0;
+    const float* src = (const float*)typed_data(env, v, &bytes);
+    if (!src || bytes < n * sizeof(float)) return 0;
+    memcpy(dst, src, n * sizeof(float));
+    return 1;
+}
+static int grid_prop(napi_env env, napi_value obj, const char* key, rt_grid* g) {   /* 1 = present */
+    napi_value v;
+    napi_valuetype vt = napi_undefined;
+    memset(g, 0, sizeof *g);
+    if (napi_get_named_property(env, obj, key, &v) != napi_ok || napi_typeof(env, v, &vt) != napi_ok || vt != napi_object) return 0;
+    grid_from_js(env, v, g);
+    return g->prim != NULL;
+}
+static napi_value js_a089_render_frame(napi_env env, napi_callback_info info) {
+    napi_value a[5], lp;
+    rt_a089_frame f;
+    rt_grid gs, gt;
+    if (!get_args(env, info, 5, a)) return NULL;
+    memset(&f, 0, sizeof f);
+    if (grid_prop(env, a[1], "spheres", &gs)) {
+        f.spheres = gs.prim; f.s_matid = gs.matid; f.s_box_size = gs.box_size; f.s_n_slabs = gs.n_slabs;
+        if (!copy_floats(env, a[1], "s_bound", f.s_bound, 8)) return rt_throw(env, RT_ERR_INVALID);
+    }
+    if (grid_prop(env, a[1], "triangles", &gt)) {
+        f.t_pos = gt.prim; f.t_normal = gt.normal; f.t_matid = gt.matid; f.t_box_size = gt.box_size; f.t_n_slabs = gt.n_slabs;
+        if (!copy_floats(env, a[1], "t_bound", f.t_bound, 8) || !copy_floats(env, a[1], "t_shadow_bound", f.t_shadow_bound, 8))
+            return rt_throw(env, RT_ERR_INVALID);
+    }
+    f.material = get_handle_prop(env, a[1], "material");
+    f.n_lights = (unsigned)get_num(env, a[1], "n_lights", 0);
+    f.light_pos = napi_get_named_property(env, a[1], "light_pos", &lp) == napi_ok ? (const float*)typed_or_null(env, lp) : NULL;
+    if (!copy_floats(env, a[1], "bound", f.bound, 8) || !copy_floats(env, a[1], "fcam", f.fcam, 16)) return rt_throw(env, RT_ERR_INVALID);
+    f.focal_length = (float)get_num(env, a[1], "focal_length", 1.0);
+    f.lens_rad = (float)get_num(env, a[1], "lens_rad", 0.0);
+    f.rays_per_pixel = (unsigned)get_num(env, a[1], "rays_per_pixel", 1);
+    f.thin_lens = (unsigned)get_num(env, a[1], "thin_lens", 0);
+    int rc = rt_a089_render_frame((rt_ctx*)get_handle(env, a[0]), &f, get_handle(env, a[2]), get_handle(env, a[3]), get_handle(env, a[4]));
+    return rc ? rt_throw(env, rc) : NULL;
+}
+
 /* ---- everything with a uniform signature (launchers, buffers, scene setters, render object) ---- */
 #include "rt2015_napi_gen.inc"
 
@@ -436,6 +484,7 @@ napi_value rt2015_init(napi_env env, napi_value exports) {
         {"slab_build_triangles", js_slab_build_triangles}, {"grid_release", js_grid_release}, {"parse_mesh_json", js_parse_mesh_json},
         {"parse_pdb", js_parse_pdb}, {"scene_create", js_scene_create}, {"scene_add_set", js_scene_add_set},
         {"render_create", js_render_create}, {"render_accum_image", js_render_accum_image}, {"render_stats", js_render_stats},
+        {"a089_render_frame", js_a089_render_frame},
         RT2015_GENERATED_EXPORTS
     };
     for (size_t i = 0; i < sizeof table / sizeof table[0]; i++) {

@@ -153,6 +153,24 @@ int rt_a09_triangleShadowTrace(rt_ctx*, unsigned total_rays, void* shadow_rays, 
 int rt_a09_sceneRender(rt_ctx*, void* acu, void* pois, const void* shadow_rays, const void* material, unsigned total_rays);
 int rt_a09_copyToPixel(rt_ctx*, void* pixel, const void* acu, float m, unsigned pixels, unsigned rays_per_pixel);   /* A09/code.cl:1023-1040 */
 
+/* The whole deterministic frame of Assignment 8 / 9 in ONE launch (ours: render() of A08/code.js:1194-1232 and
+ * A09/code.js:1256-1294 without the per-kernel round trips of 48-byte Ray / Poi records through memory): primary ray
+ * (pinhole, or thin lens when `thin_lens`), closest hit over the sphere and triangle grids, per point light a shadow ray
+ * with any-hit traces and sceneRender -- the accumulator of every slot, bit for bit what the launcher sequence leaves in
+ * `acu`.  Follow it with rt_a08_copyToPixel / rt_a09_copyToPixel.  Absent sets: spheres / t_pos = NULL.  All pointers are
+ * device pointers except light_pos (host, 4 floats per light, at most 16 lights). */
+typedef struct {
+    const void* spheres; const void* s_matid; const void* s_box_size; float s_bound[8]; unsigned s_n_slabs;
+    const void* t_pos; const void* t_normal; const void* t_matid; const void* t_box_size; float t_bound[8]; unsigned t_n_slabs;
+    float t_shadow_bound[8];      /* bound handed to triangleShadowTrace: the SPHERE bounds in A08 (A08/code.js:918), t_bound in A09 */
+    const void* material;
+    const float* light_pos; unsigned n_lights;
+    float bound[8]; float fcam[16];
+    float focal_length, lens_rad; unsigned rays_per_pixel; unsigned thin_lens;
+} rt_a089_frame;
+/* out_matid (int per slot) / out_maxt (float per slot): optional hit record outputs, may be NULL */
+int rt_a089_render_frame(rt_ctx*, const rt_a089_frame* frame, void* acu, void* out_matid, void* out_maxt);
+
 /* Optional per-work-item statistics for the five grid-walk launchers (all device pointers,
  * any may be NULL; pass all NULL to switch off): winning reference index (0xFFFFFFFF =
  * none), cells visited, primitive tests.  Used for hit-id parity and for the algorithmic

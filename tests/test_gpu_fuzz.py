@@ -128,3 +128,7 @@ def test_random_scene_a08_a09_match_oracle(rt, gpu_ctx, ref_lib, tmp_path, case)
         assert np.array_equal(maxt[hit].view(np.uint32), st["rays"]["maxt"][hit].view(np.uint32)), "A%02d case %d: hit distances" % (a, case)
         assert np.array_equal(acu.view(np.uint32), np.ascontiguousarray(acu_o, dtype=np.float32).view(np.uint32)), "A%02d case %d: float image" % (a, case)
         assert np.array_equal(pix.reshape(-1, 4), np.asarray(pix_o).reshape(-1, 4)), "A%02d case %d: pixels" % (a, case)
+        acu_f, pix_f, matid_f, maxt_f = rt.assignments.a089_render_fused(gpu_ctx, p_scene, COLS, ROWS, a, 4, n_slabs)
+        assert np.array_equal(acu_f.view(np.uint32), acu.view(np.uint32)) and np.array_equal(matid_f, matid) and np.array_equal(pix_f, pix), \
+            "A%02d case %d: one-launch frame differs from the launcher sequence" % (a, case)
+        assert np.array_equal(maxt_f[hit].view(np.uint32), maxt[hit].view(np.uint32))

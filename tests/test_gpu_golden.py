@@ -143,6 +143,10 @@ def test_a08_a09_scene(rt, gpu_ctx, tmp_path, name):
     hit = fx["matid"] >= 0
     assert np.array_equal(maxt[hit].view(np.uint32), fx["maxt"][hit].view(np.uint32))
     _same_pixels(pix, fx["pixels"], "uchar image")
+    # the whole frame in one launch (rt_a089_render_frame) leaves the same accumulators, hit records and pixels
+    acu_f, pix_f, matid_f, maxt_f = rt.assignments.a089_render_fused(gpu_ctx, scene, P["cols"], P["rows"], P["assignment"], P["rpp"], P["n_slabs"])
+    assert np.array_equal(acu_f.view(np.uint32), acu.view(np.uint32)) and np.array_equal(matid_f, matid) and np.array_equal(pix_f, pix)
+    assert np.array_equal(maxt_f[hit].view(np.uint32), maxt[hit].view(np.uint32))
 
 
 @pytest.mark.parametrize("mode", [0, 1])
