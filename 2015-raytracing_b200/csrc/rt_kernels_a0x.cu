@@ -99,9 +99,82 @@ RT_DEV bool interSphereA02(f3 o, f3 d, float a, float mint, float maxt, float4 s
     return false;
 }
 
+// Sphere loop on Blackwell's packed fp32 pipe (RT_PACKED_F32X2, default on).  FADD2 / FMUL2 (PTX add.f32x2 / mul.f32x2,
+// sm_100+) perform two independent round-to-nearest operations per lane and issue slot, so one iteration evaluates the
+// discriminant of TWO consecutive spheres (multiplications and the sums of non-products packed): tiles are staged as pairs, component-wise and pre-negated -- (-cx_j, -cx_j+1),
+// ..., (-r^2_j, -r^2_j+1) -- and the subtraction chain of interSphere becomes additions of exact negatives
+// (a - b == a + (-b), 2*x == x + x, -(p*q) == (-p)*q in IEEE arithmetic), so every discriminant has the bits of the scalar
+// form.  A sphere whose discriminant is not negative (rare) goes through the scalar test, in index order.
+#ifndef RT_PACKED_F32X2
+#define RT_PACKED_F32X2 1
+#endif
+RT_DEV BruteHit bruteForcePacked(bool live, f3 o, f3 d, float mint, float maxt, unsigned s_size, const float4* __restrict__ s_atoms, float4* tile) {
+    BruteHit h;
+    h.t = RT_INF;
+    h.i = s_size;
+    const float a = dot(d, d);
+    const float a4n = -(4.0f * a);
+    float* tnx = reinterpret_cast<float*>(tile);          // [kSphereTile] -cx, read as float2 pairs
+    float* tny = tnx + kSphereTile;
+    float* tnz = tny + kSphereTile;
+    float* tnw = tnz + kSphereTile;                       // -(r*r)
+    const float2 ox = make_float2(o.x, o.x), oy = make_float2(o.y, o.y), oz = make_float2(o.z, o.z);
+    const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
+    const float2 a4 = make_float2(a4n, a4n);
+    for (unsigned base = 0; base < s_size; base += kSphereTile) {
+        const unsigned n = min(kSphereTile, s_size - base);
+        const unsigned n2 = (n + 1u) & ~1u;
+        __syncthreads();
+        for (unsigned j = threadIdx.x; j < n2; j += blockDim.x) {
+            if (j < n) {
+                float4 s = __ldg(s_atoms + base + j);
+                tnx[j] = -s.x; tny[j] = -s.y; tnz[j] = -s.z; tnw[j] = -(s.w * s.w);
+            } else {   // padding of an odd tile: c = +inf makes the discriminant -inf, never a hit
+                tnx[j] = 0.f; tny[j] = 0.f; tnz[j] = 0.f; tnw[j] = RT_INF;
+            }
+        }
+        __syncthreads();
+        if (live) {
+            const float2* px = reinterpret_cast<const float2*>(tnx);
+            const float2* py = reinterpret_cast<const float2*>(tny);
+            const float2* pz = reinterpret_cast<const float2*>(tnz);
+            const float2* pw = reinterpret_cast<const float2*>(tnw);
+#pragma unroll 2
+            for (unsigned q = 0; q < n2 / 2; q++) {
+                // Products are added with SCALAR adds: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under
+                // --fmad=false (it keeps scalar mul.rn / add.rn apart), and a fused product would change the rounding.  Sums
+                // of non-products (o - c, dt + dt, mm - r*r) stay packed.
+                const float2 mx = __fadd2_rn(ox, px[q]), my = __fadd2_rn(oy, py[q]), mz = __fadd2_rn(oz, pz[q]);   // o - c
+                const float2 p0 = __fmul2_rn(mx, dx), p1 = __fmul2_rn(my, dy), p2 = __fmul2_rn(mz, dz);
+                const float2 dt = make_float2(__fadd_rn(__fadd_rn(p0.x, p1.x), p2.x), __fadd_rn(__fadd_rn(p0.y, p1.y), p2.y));
+                const float2 b = __fadd2_rn(dt, dt);                                                               // 2 * dot(omc, d)
+                const float2 s0 = __fmul2_rn(mx, mx), s1 = __fmul2_rn(my, my), s2 = __fmul2_rn(mz, mz);
+                const float2 mm = make_float2(__fadd_rn(__fadd_rn(s0.x, s1.x), s2.x), __fadd_rn(__fadd_rn(s0.y, s1.y), s2.y));
+                const float2 c = __fadd2_rn(mm, pw[q]);                                                            // dot(omc, omc) - r*r
+                const float2 bb = __fmul2_rn(b, b), ac = __fmul2_rn(a4, c);
+                const float2 dis = make_float2(__fadd_rn(bb.x, ac.x), __fadd_rn(bb.y, ac.y));                      // b*b - 4*a*c
+                if (!(dis.x < 0.0f)) {
+                    float t;
+                    const unsigned j = 2 * q;
+                    if (interSphereA02(o, d, a, mint, maxt, make_float4(-tnx[j], -tny[j], -tnz[j], -tnw[j]), t) && t < h.t) { h.t = t; h.i = base + j; }
+                }
+                if (!(dis.y < 0.0f)) {
+                    float t;
+                    const unsigned j = 2 * q + 1;
+                    if (j < n && interSphereA02(o, d, a, mint, maxt, make_float4(-tnx[j], -tny[j], -tnz[j], -tnw[j]), t) && t < h.t) { h.t = t; h.i = base + j; }
+                }
+            }
+        }
+    }
+    return h;
+}
+
 // every thread of the block must call this (barriers inside); `live` lanes own a ray; (mint, maxt) is the ray's
 // EXCLUSIVE parameter range (0, +inf for a fresh primary ray)
 RT_DEV BruteHit bruteForce(bool live, f3 o, f3 d, float mint, float maxt, unsigned s_size, const float4* __restrict__ s_atoms, float4* tile) {
+#if RT_PACKED_F32X2
+    return bruteForcePacked(live, o, d, mint, maxt, s_size, s_atoms, tile);
+#else
     BruteHit h;
     h.t = RT_INF;
     h.i = s_size;
@@ -124,6 +197,7 @@ RT_DEV BruteHit bruteForce(bool live, f3 o, f3 d, float mint, float maxt, unsign
         }
     }
     return h;
+#endif
 }
 
 // pinhole ray of A02-A10 (getRay, A02/code.cl:78-90 = A10/code.cl:108-119)
