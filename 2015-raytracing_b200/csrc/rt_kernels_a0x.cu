@@ -114,10 +114,8 @@ RT_DEV BruteHit bruteForcePacked(bool live, f3 o, f3 d, float mint, float maxt, 
     h.i = s_size;
     const float a = dot(d, d);
     const float a4n = -(4.0f * a);
-    float* tnx = reinterpret_cast<float*>(tile);          // [kSphereTile] -cx, read as float2 pairs
-    float* tny = tnx + kSphereTile;
-    float* tnz = tny + kSphereTile;
-    float* tnw = tnz + kSphereTile;                       // -(r*r)
+    // pair q of the tile = two float4: (-cx_j, -cx_j+1, -cy_j, -cy_j+1) and (-cz_j, -cz_j+1, -r2_j, -r2_j+1), j = 2q: two LDS.128 per pair
+    float* tf = reinterpret_cast<float*>(tile);
     const float2 ox = make_float2(o.x, o.x), oy = make_float2(o.y, o.y), oz = make_float2(o.z, o.z);
     const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
     const float2 a4 = make_float2(a4n, a4n);
@@ -126,42 +124,41 @@ RT_DEV BruteHit bruteForcePacked(bool live, f3 o, f3 d, float mint, float maxt, 
         const unsigned n2 = (n + 1u) & ~1u;
         __syncthreads();
         for (unsigned j = threadIdx.x; j < n2; j += blockDim.x) {
+            float* slot = tf + 8 * (j >> 1) + (j & 1);
             if (j < n) {
                 float4 s = __ldg(s_atoms + base + j);
-                tnx[j] = -s.x; tny[j] = -s.y; tnz[j] = -s.z; tnw[j] = -(s.w * s.w);
+                slot[0] = -s.x; slot[2] = -s.y; slot[4] = -s.z; slot[6] = -(s.w * s.w);
             } else {   // padding of an odd tile: c = +inf makes the discriminant -inf, never a hit
-                tnx[j] = 0.f; tny[j] = 0.f; tnz[j] = 0.f; tnw[j] = RT_INF;
+                slot[0] = 0.f; slot[2] = 0.f; slot[4] = 0.f; slot[6] = RT_INF;
             }
         }
         __syncthreads();
         if (live) {
-            const float2* px = reinterpret_cast<const float2*>(tnx);
-            const float2* py = reinterpret_cast<const float2*>(tny);
-            const float2* pz = reinterpret_cast<const float2*>(tnz);
-            const float2* pw = reinterpret_cast<const float2*>(tnw);
 #pragma unroll 2
             for (unsigned q = 0; q < n2 / 2; q++) {
+                const float4 A = tile[2 * q], B = tile[2 * q + 1];
+                const float2 pxq = make_float2(A.x, A.y), pyq = make_float2(A.z, A.w), pzq = make_float2(B.x, B.y), pwq = make_float2(B.z, B.w);
                 // Products are added with SCALAR adds: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under
                 // --fmad=false (it keeps scalar mul.rn / add.rn apart), and a fused product would change the rounding.  Sums
                 // of non-products (o - c, dt + dt, mm - r*r) stay packed.
-                const float2 mx = __fadd2_rn(ox, px[q]), my = __fadd2_rn(oy, py[q]), mz = __fadd2_rn(oz, pz[q]);   // o - c
+                const float2 mx = __fadd2_rn(ox, pxq), my = __fadd2_rn(oy, pyq), mz = __fadd2_rn(oz, pzq);   // o - c
                 const float2 p0 = __fmul2_rn(mx, dx), p1 = __fmul2_rn(my, dy), p2 = __fmul2_rn(mz, dz);
                 const float2 dt = make_float2(__fadd_rn(__fadd_rn(p0.x, p1.x), p2.x), __fadd_rn(__fadd_rn(p0.y, p1.y), p2.y));
                 const float2 b = __fadd2_rn(dt, dt);                                                               // 2 * dot(omc, d)
                 const float2 s0 = __fmul2_rn(mx, mx), s1 = __fmul2_rn(my, my), s2 = __fmul2_rn(mz, mz);
                 const float2 mm = make_float2(__fadd_rn(__fadd_rn(s0.x, s1.x), s2.x), __fadd_rn(__fadd_rn(s0.y, s1.y), s2.y));
-                const float2 c = __fadd2_rn(mm, pw[q]);                                                            // dot(omc, omc) - r*r
+                const float2 c = __fadd2_rn(mm, pwq);                                                              // dot(omc, omc) - r*r
                 const float2 bb = __fmul2_rn(b, b), ac = __fmul2_rn(a4, c);
                 const float2 dis = make_float2(__fadd_rn(bb.x, ac.x), __fadd_rn(bb.y, ac.y));                      // b*b - 4*a*c
                 if (!(dis.x < 0.0f)) {
                     float t;
                     const unsigned j = 2 * q;
-                    if (interSphereA02(o, d, a, mint, maxt, make_float4(-tnx[j], -tny[j], -tnz[j], -tnw[j]), t) && t < h.t) { h.t = t; h.i = base + j; }
+                    if (interSphereA02(o, d, a, mint, maxt, make_float4(-A.x, -A.z, -B.x, -B.z), t) && t < h.t) { h.t = t; h.i = base + j; }
                 }
                 if (!(dis.y < 0.0f)) {
                     float t;
                     const unsigned j = 2 * q + 1;
-                    if (j < n && interSphereA02(o, d, a, mint, maxt, make_float4(-tnx[j], -tny[j], -tnz[j], -tnw[j]), t) && t < h.t) { h.t = t; h.i = base + j; }
+                    if (j < n && interSphereA02(o, d, a, mint, maxt, make_float4(-A.y, -A.w, -B.y, -B.w), t) && t < h.t) { h.t = t; h.i = base + j; }
                 }
             }
         }
