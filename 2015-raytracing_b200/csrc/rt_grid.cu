@@ -411,6 +411,7 @@ int buildGrid(rt_ctx* ctx, int kind, const double* prim_host, const double* nor_
         RT_LAUNCH_CHECK(ctx, "grid_gather");
     }
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->grids.push_back({out->box_size, (const unsigned*)out->occupancy});
     return RT_OK;
 }
 
@@ -445,6 +446,8 @@ int rt_grid_release(rt_ctx* ctx, rt_grid* g) {
     if (!g) return RT_ERR_INVALID;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->grids.size(); i++)
+        if (ctx->grids[i].first == g->box_size) { ctx->grids.erase(ctx->grids.begin() + i); break; }
     cudaFree(g->prim);
     cudaFree(g->normal);
     cudaFree(g->matid);

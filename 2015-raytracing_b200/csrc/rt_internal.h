@@ -23,7 +23,17 @@ struct rt_ctx {
     // between calls: the device's default pool releases everything at each synchronisation, which made a per-pass
     // 16 MB cudaMallocAsync cost 27 ms
     cudaMemPool_t pool = nullptr;
+    // cell tables of the grids built through this context -> their occupancy bitmaps (1 bit per non-empty cell).  The
+    // launchers keep the reference kernels' argument lists (which only know the cell table), look the bitmap up here and,
+    // when the table is one of ours, skip the two table loads of every EMPTY cell a ray crosses -- same walk, same floats.
+    std::vector<std::pair<const void*, const unsigned*>> grids;
 };
+
+static inline const unsigned* rt_occupancy_of(const rt_ctx* ctx, const void* box_size) {
+    for (const auto& g : ctx->grids)
+        if (g.first == box_size) return g.second;
+    return nullptr;
+}
 
 static inline cudaError_t rt_scratch_alloc(rt_ctx* ctx, void** p, size_t bytes) {
     return ctx->pool ? cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);

@@ -22,11 +22,11 @@ RT_DEV uchar4 mkPixel(float r, float g, float b) { return make_uchar4(f2uc(r), f
 
 AabbArg mkAabb(const float* b) { AabbArg a; memcpy(a.v, b, sizeof a.v); return a; }
 CamArg mkCam(const float* c) { CamArg a; memcpy(a.v, c, sizeof a.v); return a; }
-GridView mkGrid(const void* prim, const void* box, const float* bound, unsigned n) {
+GridView mkGrid(const void* prim, const void* box, const float* bound, unsigned n, const unsigned* occ = nullptr) {
     GridView g;
     g.prim = (const float4*)prim;
     g.box = (const unsigned*)box;
-    g.occ = nullptr;
+    g.occ = n > 1 ? occ : nullptr;   // occupancy bitmap of a grid built by rt_grid_build_* (rt_occupancy_of), else none
     g.bound.pmin = f3{bound[0], bound[1], bound[2]};
     g.bound.pmax = f3{bound[4], bound[5], bound[6]};
     g.n = n;
@@ -476,7 +476,7 @@ RT_DEV uchar4 cellParityColor(const Hit& h, float shade) {
     return mkPixel((float)((h.cx % 2) + 1) * s, (float)((h.cy % 2) + 1) * s, (float)((h.cz % 2) + 1) * s);
 }
 
-template <int PRIM>
+template <int PRIM, bool OCC>
 __global__ void k_a07_trace(uchar4* pixels, CamArg fcam, Ray* rays, GridView g, const float4* normals) {
     unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     Camera cam = floatToCamera(fcam.v);
@@ -486,7 +486,7 @@ __global__ void k_a07_trace(uchar4* pixels, CamArg fcam, Ray* rays, GridView g, 
     AabbHit binter = interAABB(ray.o, ray.d, g.bound);
     if (!binter.v) return;
     // spheres: inclusive test; triangles: EXCLUSIVE in A07 (A07/code.cl:195, quirk Q9)
-    Hit h = gridWalk<PRIM, false, false, false>(ray.o, ray.d, ray.maxt, g, binter, nullptr);
+    Hit h = gridWalk<PRIM, false, false, false, OCC>(ray.o, ray.d, ray.maxt, g, binter, nullptr);
     if (h.i == 0xFFFFFFFFu) return;
     rays[id].maxt = h.t;
     float shade;
@@ -897,7 +897,9 @@ int rt_a07_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, un
     if (!pixels || !fcam || !rays || !s_atoms || !bound || !n_slabs || !slab_size) return RT_ERR_INVALID;
     size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
     if (!n) return RT_OK;
-    k_a07_trace<PRIM_SPHERE><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, mkGrid(s_atoms, slab_size, bound, n_slabs), nullptr);
+    GridView g = mkGrid(s_atoms, slab_size, bound, n_slabs, rt_occupancy_of(ctx, slab_size));
+    if (g.occ) k_a07_trace<PRIM_SPHERE, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, nullptr);
+    else k_a07_trace<PRIM_SPHERE, false><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, nullptr);
     RT_LAUNCH_CHECK(ctx, "A07 molTrace");
     return RT_OK;
 }
@@ -909,8 +911,9 @@ int rt_a07_meshTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, u
     if (!pixels || !fcam || !rays || !t_pos || !t_normal || !bound || !n_slabs || !slab_size) return RT_ERR_INVALID;
     size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
     if (!n) return RT_OK;
-    k_a07_trace<PRIM_TRIANGLE><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, mkGrid(t_pos, slab_size, bound, n_slabs),
-                                                (const float4*)t_normal);
+    GridView g = mkGrid(t_pos, slab_size, bound, n_slabs, rt_occupancy_of(ctx, slab_size));
+    if (g.occ) k_a07_trace<PRIM_TRIANGLE, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)t_normal);
+    else k_a07_trace<PRIM_TRIANGLE, false><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)t_normal);
     RT_LAUNCH_CHECK(ctx, "A07 meshTrace");
     return RT_OK;
 }
