@@ -324,16 +324,21 @@ RT_DEV bool interTrianglePre(f3 o, f3 d, float mint, float maxt, float div, f3 p
 }
 
 // The same test once more, arranged for throughput: the two cheap sign rejections come BEFORE the
-// IEEE division.  Equivalent decisions and identical floats: with div > 0 the reciprocal idiv is in
-// (0, +inf], so beta = nb * idiv < 0  <=>  nb < 0 and gamma = ngm * idiv < 0  <=>  ngm < 0 (a NaN
-// numerator fails both comparisons on either route; div = +inf, where idiv = 0 would turn a negative
-// numerator into -0, is excluded by the guard).  Rejections have no side effects, so their order is free.
+// IEEE division.  With div > 0 the reciprocal idiv = RN(1 / div) is positive, so beta = nb * idiv is negative
+// exactly when nb is -- UNLESS the product underflows to -0, which the reference's `beta < 0` does not
+// reject.  The early exit is therefore taken only where underflow is impossible: |numerator| >= FLT_MIN
+// (2^-126) and div <= 2^22 give |numerator * idiv| >= 2^-126 * 2^-22 = 2^-148, a non-zero subnormal of the
+// numerator's sign.  Everything else (tiny numerators, huge or infinite div, NaNs) falls through to the
+// reference's own order of operations below.  Rejections have no side effects, so their order is free.
+// Checked against interTriangle<true> on subnormal numerators and huge divisors in tests/tri_fast_check.cu.
+constexpr float kFastDivMax = 4194304.0f;          // 2^22
+constexpr float kFastNumMin = 1.17549435e-38f;     // FLT_MIN = 2^-126
 RT_DEV bool interTriangleFast(f3 o, f3 d, float mint, float maxt, float div, f3 p0, f3 e1, f3 e2, float& beta_o, float& gamma_o, float& t_out) {
     if (div <= 0) return false;
     f3 s = o - p0;
     float nb = dot(cross(s, d), e2);
     float ngm = dot(cross(s, e1), d);
-    if ((nb < 0.0f || ngm < 0.0f) && div < RT_INF) return false;
+    if ((nb <= -kFastNumMin || ngm <= -kFastNumMin) && div <= kFastDivMax) return false;
     float idiv = 1.0f / div;
     float beta = nb * idiv;
     if (beta < 0.0f || beta > 1.0f) return false;
@@ -725,7 +730,7 @@ RT_DEV Hit singleCellWalk(f3 o, f3 d, float maxt_in, const GridView& g, const fl
     // SAME references but reject them at different points) do not serialise each other's rejections:
     //   1. face-vector cull for every reference (uniform, cheap)            -> bit mask of front-facing ones
     //   2. the two barycentric numerators for the survivors (each lane walks ITS OWN set bits) -> mask of
-    //      references with both numerators non-negative (interTriangleFast's sign rejections)
+    //      references that survive interTriangleFast's sign rejections (numerator <= -2^-126 with div <= 2^22)
     //   3. the division and the range tests for what is left, in ascending reference order, applying the
     //      reference's `inter.v && inter.t < champ_t` update (and the any-hit break) exactly as the plain loop does.
     // Rejections have no side effects, so the outcome (winner and floats) is that of the sequential loop.
@@ -736,7 +741,7 @@ RT_DEV Hit singleCellWalk(f3 o, f3 d, float maxt_in, const GridView& g, const fl
             float4 q = __ldg(pre_ng + base + j);
             float dv = dot(mk3(q.x, q.y, q.z), d);
             if (dv > 0) m1 |= 1u << j;
-            if (dv == RT_INF) minf |= 1u << j;   // interTriangleFast does not apply the sign rejections then
+            if (dv > kFastDivMax) minf |= 1u << j;   // interTriangleFast does not apply the sign rejections then
         }
         unsigned m2 = minf;
         for (unsigned m = m1 & ~minf; m; m &= m - 1) {
@@ -745,7 +750,7 @@ RT_DEV Hit singleCellWalk(f3 o, f3 d, float maxt_in, const GridView& g, const fl
             f3 s = o - mk3(q0.x, q0.y, q0.z);
             float nb = dot(cross(s, d), mk3(q2.x, q2.y, q2.z));
             float ngm = dot(cross(s, mk3(q1.x, q1.y, q1.z)), d);
-            if (!(nb < 0.0f || ngm < 0.0f)) m2 |= 1u << j;
+            if (!(nb <= -kFastNumMin || ngm <= -kFastNumMin)) m2 |= 1u << j;
         }
         bool stop = false;
         for (unsigned m = m2; m; m &= m - 1) {

@@ -2,7 +2,8 @@
 // Mirrors preRender / executeRender / postRender of Assign10-Path_Tracing/code.js:1784-1859.
 //
 // Ray slots are independent (every reference kernel indexes only its own slot id), so the
-// frame is processed in TILES of consecutive slots whose ray/hit/shadow state fits the L2;
+// frame is processed in TILES of consecutive slots (a quarter of device memory by default, see
+// rt_render_create: the queue walkers want deep queues, the state streams through HBM either way);
 // only the per-slot seed and accumulation buffers persist across passes, exactly as in the
 // reference (acu is never cleared between passes, A10/code.js:1078-1099).
 #include "rt_frame.h"
@@ -136,6 +137,14 @@ __global__ void f_macroOccupancy(const unsigned* occ, unsigned n, unsigned sh, u
     if ((threadIdx.x & 31) == 0 && (m >> 5) < 8192) macro[m >> 5] = bits;
 }
 
+// Occupancy bits of a cell table that came without them (a grid the caller built): bit c = cell c is non-empty.
+__global__ void f_occupancyFromTable(const unsigned* box, size_t cells, unsigned* occ) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool full = c < cells && box[c + 1] > box[c];
+    unsigned bits = __ballot_sync(0xffffffffu, full);
+    if ((threadIdx.x & 31) == 0 && c < cells) occ[c >> 5] = bits;
+}
+
 #define RT_TRY(expr)              \
     do {                          \
         int _rc = (expr);         \
@@ -238,6 +247,7 @@ int rt_scene_destroy(rt_scene* s) {
         if (st.pre_ng) rt_buffer_release(s->ctx, st.pre_ng);
         if (st.pre_pe) rt_buffer_release(s->ctx, st.pre_pe);
         if (st.macro_occ) rt_buffer_release(s->ctx, st.macro_occ);
+        if (st.own_occ) rt_buffer_release(s->ctx, st.own_occ);
     }
     delete s;
     return RT_OK;
@@ -266,7 +276,18 @@ int rt_scene_add_set(rt_scene* s, const rt_grid* grid, const float bound[8], int
     memcpy(st.bound, bound, sizeof st.bound);
     st.is_mesh = is_mesh;
     st.mesh_matid = mesh_matid;
-    if (grid->n_slabs > 1 && grid->occupancy) {   // multi-cell ("heavy") set: coarse occupancy for the queue walkers
+    if (grid->n_slabs > 1 && !grid->occupancy) {
+        // a caller-built grid (the drop-in ABI accepts any box_size / prim buffers): the fused paths walk multi-cell
+        // grids through the occupancy bits, so derive them from the cell table here (owned by the scene)
+        rt_ctx* ctx = s->ctx;
+        size_t cells = (size_t)grid->n_slabs * grid->n_slabs * grid->n_slabs;
+        RT_TRY(rt_buffer_create(ctx, sizeof(unsigned) * ((cells + 31) / 32), (void**)&st.own_occ));
+        f_occupancyFromTable<<<rt_blocks((cells + 31) / 32 * 32, kBlock), kBlock, 0, ctx->stream>>>((const unsigned*)grid->box_size, cells, st.own_occ);
+        RT_LAUNCH_CHECK(ctx, "occupancyFromTable");
+        st.grid.occupancy = st.own_occ;
+    }
+    grid = &st.grid;
+    if (grid->n_slabs > 1) {   // multi-cell ("heavy") set: coarse occupancy for the queue walkers
         rt_ctx* ctx = s->ctx;
         unsigned sh = 0;
         while (((grid->n_slabs + (1u << sh) - 1) >> sh) > 64) sh++;
@@ -308,7 +329,11 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     r->ctx = ctx;
     r->scene = scene;
     r->o = *opts;
-    if (r->o.slot_count == 0) { r->o.slot_begin = 0; r->o.slot_count = r->o.rays_per_pixel; }
+    if (r->o.slot_count == 0) {   // 0,0 = every slot; an EMPTY range at slot_begin > 0 must not silently become "all slots"
+        if (r->o.slot_begin != 0) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: empty slot range (this rank has no slots: skip the render, contribute a zero image)"); }
+        r->o.slot_count = r->o.rays_per_pixel;
+    }
+    if (r->o.mode > 2) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: mode must be 0 (wavefront), 1 (reference schedule) or 2 (megakernel)"); }
     if (r->o.slot_begin + r->o.slot_count > r->o.rays_per_pixel) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: slot range exceeds rays_per_pixel"); }
     if (r->o.rays_per_pixel > 1) {
         unsigned side = (unsigned)sqrtf((float)r->o.rays_per_pixel);

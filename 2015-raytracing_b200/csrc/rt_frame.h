@@ -18,6 +18,7 @@ struct SceneSet {
     // small enough to sit in shared memory of the queue walkers (the fine bitmap is n^3 bits)
     unsigned* macro_occ = nullptr;
     unsigned macro_shift = 0, macro_n = 0;
+    unsigned* own_occ = nullptr;   // occupancy bits derived here for a caller-built grid that came without (rt_scene_add_set)
 };
 struct SceneLight { float shadow[16], scene[16], light[16]; };
 

@@ -281,7 +281,7 @@ RT_DEV bool interTriangleExcl(f3 o, f3 d, float mint, float maxt, float div, f3 
     f3 s = o - p0;
     float nb = dot(cross(s, d), e2);
     float ngm = dot(cross(s, e1), d);
-    if ((nb < 0.0f || ngm < 0.0f) && div < RT_INF) return false;
+    if ((nb <= -kFastNumMin || ngm <= -kFastNumMin) && div <= kFastDivMax) return false;   // only where nb * idiv cannot underflow to -0 (rt_device.cuh)
     float idiv = 1.0f / div;
     float beta = nb * idiv;
     if (beta < 0.0f || beta > 1.0f) return false;
@@ -476,17 +476,31 @@ RT_DEV uchar4 cellParityColor(const Hit& h, float shade) {
     return mkPixel((float)((h.cx % 2) + 1) * s, (float)((h.cy % 2) + 1) * s, (float)((h.cz % 2) + 1) * s);
 }
 
-template <int PRIM, bool OCC>
-__global__ void k_a07_trace(uchar4* pixels, CamArg fcam, Ray* rays, GridView g, const float4* normals) {
+// Optional per-pixel statistics sinks of rt_set_walk_stats (hit-id parity, work counters of the roofline).
+struct A07Stats { unsigned* hit; unsigned* cells; unsigned* tests; };
+
+template <int PRIM, bool OCC, bool STATS>
+__global__ void k_a07_trace(uchar4* pixels, CamArg fcam, Ray* rays, GridView g, const float4* normals, A07Stats sp) {
     unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     Camera cam = floatToCamera(fcam.v);
     if (id >= cam.cols * cam.rows) return;
+    if (STATS) {
+        if (sp.hit) sp.hit[id] = 0xFFFFFFFFu;
+        if (sp.cells) sp.cells[id] = 0;
+        if (sp.tests) sp.tests[id] = 0;
+    }
     RayR ray = loadRay(rays + id);
     if (ray.mint == ray.maxt) return;
     AabbHit binter = interAABB(ray.o, ray.d, g.bound);
     if (!binter.v) return;
     // spheres: inclusive test; triangles: EXCLUSIVE in A07 (A07/code.cl:195, quirk Q9)
-    Hit h = gridWalk<PRIM, false, false, false, OCC>(ray.o, ray.d, ray.maxt, g, binter, nullptr);
+    WalkStats ws = {0, 0};
+    Hit h = gridWalk<PRIM, false, false, STATS, OCC>(ray.o, ray.d, ray.maxt, g, binter, &ws);
+    if (STATS) {
+        if (sp.hit) sp.hit[id] = h.i;
+        if (sp.cells) sp.cells[id] = (unsigned)ws.cells;
+        if (sp.tests) sp.tests[id] = (unsigned)ws.tests;
+    }
     if (h.i == 0xFFFFFFFFu) return;
     rays[id].maxt = h.t;
     float shade;
@@ -752,6 +766,19 @@ __global__ void __launch_bounds__(kBlock) k_a089_frame(const __grid_constant__ A
 
 #define RT_GRID1(n) rt_blocks((n), kBlock), kBlock, 0, ctx->stream
 
+template <int PRIM>
+void launchA07(rt_ctx* ctx, size_t n, void* pixels, const float* fcam, void* rays, const GridView& g, const void* normals) {
+    A07Stats sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests};
+    const bool stats = sp.hit || sp.cells || sp.tests;
+    if (stats) {
+        if (g.occ) k_a07_trace<PRIM, true, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)normals, sp);
+        else k_a07_trace<PRIM, false, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)normals, sp);
+    } else {
+        if (g.occ) k_a07_trace<PRIM, true, false><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)normals, sp);
+        else k_a07_trace<PRIM, false, false><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)normals, sp);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -898,8 +925,7 @@ int rt_a07_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, un
     size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
     if (!n) return RT_OK;
     GridView g = mkGrid(s_atoms, slab_size, bound, n_slabs, rt_occupancy_of(ctx, slab_size));
-    if (g.occ) k_a07_trace<PRIM_SPHERE, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, nullptr);
-    else k_a07_trace<PRIM_SPHERE, false><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, nullptr);
+    launchA07<PRIM_SPHERE>(ctx, n, pixels, fcam, rays, g, nullptr);
     RT_LAUNCH_CHECK(ctx, "A07 molTrace");
     return RT_OK;
 }
@@ -912,8 +938,7 @@ int rt_a07_meshTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, u
     size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
     if (!n) return RT_OK;
     GridView g = mkGrid(t_pos, slab_size, bound, n_slabs, rt_occupancy_of(ctx, slab_size));
-    if (g.occ) k_a07_trace<PRIM_TRIANGLE, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)t_normal);
-    else k_a07_trace<PRIM_TRIANGLE, false><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)t_normal);
+    launchA07<PRIM_TRIANGLE>(ctx, n, pixels, fcam, rays, g, t_normal);
     RT_LAUNCH_CHECK(ctx, "A07 meshTrace");
     return RT_OK;
 }

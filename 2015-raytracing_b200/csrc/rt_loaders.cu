@@ -84,34 +84,44 @@ struct Json {
             if (out) *out = negative ? -v : v;
             return true;
         }
+        // slow path: strtod on a NUL-terminated copy of the token (the text need not be terminated, and strtod must
+        // not read past `end`)
+        const char* t = p;
+        while (t < end && ((*t >= '0' && *t <= '9') || *t == '-' || *t == '+' || *t == '.' || *t == 'e' || *t == 'E')) t++;
+        std::string tok(p, (size_t)(t - p));
         char* e = nullptr;
-        double v = strtod(p, &e);
-        if (e == p) { fail(); return false; }
-        p = e;
+        double v = strtod(tok.c_str(), &e);
+        if (e == tok.c_str()) { fail(); return false; }
+        p += e - tok.c_str();
         if (out) *out = v;
         return true;
     }
-    void skip() {   // any value
+    bool word(const char* w) {   // literal at p, bounded by end
+        size_t n = strlen(w);
+        if ((size_t)(end - p) < n || memcmp(p, w, n) != 0) return false;
+        p += n;
+        return true;
+    }
+    static constexpr int kMaxDepth = 256;   // nesting cap of skipped values (hostile input must not overflow the stack)
+    void skip(int depth = 0) {   // any value
         ws();
-        if (p >= end) { fail(); return; }
+        if (p >= end || depth > kMaxDepth) { fail(); return; }
         if (*p == '"') { string(nullptr); return; }
         if (*p == '{') {
             p++;
             if (eat('}')) return;
-            do { string(nullptr); if (!eat(':')) { fail(); return; } skip(); } while (ok && eat(','));
+            do { string(nullptr); if (!eat(':')) { fail(); return; } skip(depth + 1); } while (ok && eat(','));
             if (!eat('}')) fail();
             return;
         }
         if (*p == '[') {
             p++;
             if (eat(']')) return;
-            do { skip(); } while (ok && eat(','));
+            do { skip(depth + 1); } while (ok && eat(','));
             if (!eat(']')) fail();
             return;
         }
-        if (!strncmp(p, "true", 4)) { p += 4; return; }
-        if (!strncmp(p, "false", 5)) { p += 5; return; }
-        if (!strncmp(p, "null", 4)) { p += 4; return; }
+        if (word("true") || word("false") || word("null")) return;
         number(nullptr);
     }
     bool numbers(std::vector<double>& v) {   // [n, n, ...]
@@ -146,6 +156,16 @@ struct JMesh { std::vector<double> pos, nor, idx; bool has_idx = false; double m
 struct JNode { std::vector<double> matrix, meshes; };
 
 inline double f32(double v) { return (double)(float)v; }   // Float32Array store
+
+// A JSON number used as an array index: a finite non-negative integer below `limit` (JavaScript would read
+// `undefined` for anything else and the loader would throw a few lines later).
+inline bool asIndex(double v, size_t limit, size_t* out) {
+    if (!(v >= 0.0) || v >= 9007199254740992.0 || v != floor(v)) return false;
+    size_t i = (size_t)v;
+    if (i >= limit) return false;
+    *out = i;
+    return true;
+}
 
 // mat3.normalFromMat4 (lib/gl-matrix.js:2723-2760) on an fp32-valued matrix, result rounded to fp32
 bool normalFromMat4(const double* a, double* out) {
@@ -238,7 +258,8 @@ int rt_parse_mesh_json(const char* text, size_t len, rt_mesh_data* out) {
         if (!normalFromMat4(m, nm)) return RT_ERR_INVALID;   // the reference dereferences the null result and throws
         size_t n_meshes = have_nodes ? nodes[k].meshes.size() : meshes.size();
         for (size_t q = 0; q < n_meshes; q++) {
-            size_t index = have_nodes ? (size_t)nodes[k].meshes[q] : q;
+            size_t index = q;
+            if (have_nodes && !asIndex(nodes[k].meshes[q], meshes.size(), &index)) return RT_ERR_INVALID;
             if (index >= meshes.size()) return RT_ERR_INVALID;
             const JMesh& mesh = meshes[index];
             const std::vector<double>& vp = mesh.pos;
@@ -249,12 +270,15 @@ int rt_parse_mesh_json(const char* text, size_t len, rt_mesh_data* out) {
                                f32(m[2] * x + m[6] * y + m[10] * z + m[14])};
                 for (int a = 0; a < 3; a++) { if (v[a] < bmin[a]) bmin[a] = v[a]; if (v[a] > bmax[a]) bmax[a] = v[a]; }
             }
+            size_t mi = 0;
+            if (!asIndex(mesh.material, 0xFFFFFFFFull, &mi)) return RT_ERR_INVALID;
+            const unsigned material = (unsigned)mi;
             size_t nV = mesh.has_idx ? mesh.idx.size() : vp.size() / 3;
             size_t nT = nV / 3;
             for (size_t i = 0; i < nT; i++) {
                 for (int c = 0; c < 3; c++) {
                     size_t vi = i * 3 + c;
-                    if (mesh.has_idx) vi = (size_t)mesh.idx[vi];
+                    if (mesh.has_idx && !asIndex(mesh.idx[vi], vp.size() / 3, &vi)) return RT_ERR_INVALID;
                     if (vi * 3 + 2 >= vp.size() || vi * 3 + 2 >= vn.size()) return RT_ERR_INVALID;
                     double x = vp[vi * 3], y = vp[vi * 3 + 1], z = vp[vi * 3 + 2];
                     P.push_back(f32(m[0] * x + m[4] * y + m[8] * z + m[12]));
@@ -265,7 +289,7 @@ int rt_parse_mesh_json(const char* text, size_t len, rt_mesh_data* out) {
                     N.push_back(f32(x * nm[1] + y * nm[4] + z * nm[7]));
                     N.push_back(f32(x * nm[2] + y * nm[5] + z * nm[8]));
                 }
-                M.push_back((unsigned)mesh.material);
+                M.push_back(material);
             }
         }
     }

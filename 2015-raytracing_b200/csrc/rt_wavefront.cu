@@ -568,108 +568,18 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
     }
 }
 
-// Persistent queue walker for one heavy set.  Each lane owns at most one ray; a lane whose walk
-// ended writes its result and becomes idle; when at least kRefill lanes of the warp are idle (or
-// none has work) the warp pops that many slot ids with ONE atomicAdd and the idle lanes set up
-// their DDA.  Every lane then advances its own ray by exactly one cell (walkCell).
+// Persistent queue walkers.  Each lane owns at most one ray; a lane whose walk ended becomes idle; when at
+// least kRefill lanes of the warp are idle (or none has work) the warp pops that many slot ids with ONE
+// atomicAdd and the idle lanes set up their DDA.
 #ifndef RT_REFILL
 #define RT_REFILL 8
 #endif
 constexpr int kRefill = RT_REFILL;
-
-template <int PRIM, bool ANY>
-__global__ void __launch_bounds__(256) k_walk(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w, unsigned n, int qslot) {
-    const unsigned lane = threadIdx.x & 31;
-    const unsigned count = w.qctr[2 * qslot];
-    unsigned* head = w.qctr + 2 * qslot + 1;
-    const float4* src = ANY ? w.sh : w.ray;
-    FlatWalker f;
-    unsigned slot = 0;
-    bool have = false;
-    bool drained = false;   // warp-uniform: the queue has no more tasks
-    while (true) {
-        unsigned idle = __ballot_sync(0xffffffffu, !have);
-        if (!drained && (__popc(idle) >= kRefill || idle == 0xffffffffu)) {
-            unsigned base = 0;
-            int leader = __ffs(idle) - 1;
-            if ((int)lane == leader) base = atomicAdd(head, (unsigned)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (!have) {
-                unsigned idx = base + __popc(idle & ((1u << lane) - 1u));
-                if (idx < count) {
-                    slot = w.queue[idx];
-                    float4 r0 = src[slot], r1 = src[n + slot];
-                    f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
-                    AabbHit binter = interAABB(o, d, set.g.bound);   // true by construction (the pusher tested it)
-                    walkInit(f.w, PRIM, o, d, r1.w, set.g, binter);
-                    flatEnter(f, set.g);
-                    have = true;
-                }
-            }
-            if (base + __popc(idle) >= count) drained = true;
-            idle = __ballot_sync(0xffffffffu, !have);
-        }
-        if (idle == 0xffffffffu) break;   // nothing left in the queue and no lane has work
-        if (have) {
-            bool done = false;
-            if (f.i < f.end) flatTest<PRIM, ANY>(f, set.g);
-            if (f.i >= f.end) {
-                done = flatLeave(f);
-                if (!done) flatEnter(f, set.g);
-            }
-            if (done) {
-                have = false;
-                const Hit& h = f.w.h;
-                if (ANY) {   // sphereShadowTrace / triangleShadowTrace tail (A10/code.cl:1185-1192)
-                    if (h.i != 0xFFFFFFFFu) {
-                        float4 s0 = w.sh[slot];
-                        w.sh[slot] = make_float4(s0.x, s0.y, s0.z, h.t);
-                        float4 s1 = w.sh[n + slot];
-                        w.sh[n + slot] = make_float4(s1.x, s1.y, s1.z, h.t);
-                    }
-                } else if (h.i != 0xFFFFFFFFu) {   // closest-hit tail (A10/code.cl:921-934)
-                    f3 p = getPoint(f.w.o, f.w.d, h.t);
-                    f3 nrm;
-                    int m;
-                    if (PRIM == PRIM_SPHERE) {
-                        float4 sp = __ldg(set.g.prim + h.i);
-                        nrm = normalize(p - mk3(sp.x, sp.y, sp.z));
-                        m = (int)__ldg(set.matid + h.i);
-                    } else {
-                        float4 n0 = __ldg(set.normals + 3 * h.i), n1 = __ldg(set.normals + 3 * h.i + 1), n2 = __ldg(set.normals + 3 * h.i + 2);
-                        nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
-                        m = set.matid ? (int)__ldg(set.matid + h.i) : (int)set.scalar_matid;
-                    }
-                    float4 r1 = w.ray[n + slot];
-                    w.ray[n + slot] = make_float4(r1.x, r1.y, r1.z, h.t);
-                    w.poi[slot] = make_float4(p.x, p.y, p.z, __int_as_float(m));
-                    w.poi[n + slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
-                }
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Warp-cooperative queue walker.  Every lane owns one ray and steps its own DDA through EMPTY
-// cells; when a lane reaches a cell that holds references, the whole warp tests that cell for
-// it: lane j takes reference begin+j, so loads are contiguous, and no lane waits on another
-// lane's fat cell.  Legal because the reference's per-cell loop (A10/code.cl:882-897) computes
-//   closest: argmin over the cell's references of (t, index) among accepted tests with t < champ_t
-//   any hit: the lowest index among accepted tests with t < champ_t
-// -- both independent of evaluation order, so the winner (and its floats) is the same.
-// Triangles are culled first on the precomputed face vector (div = dot(ng, d) <= 0 is the
-// reference's first rejection), 16 B per reference; survivors are compacted with ballot/popc
-// into a per-warp candidate list so the full test runs on dense lanes.
-// ---------------------------------------------------------------------------------------
 #ifndef RT_STEP_BURST
 #define RT_STEP_BURST 8
 #endif
 #ifndef RT_WALK_MINB
 #define RT_WALK_MINB 4
-#endif
-#ifndef RT_USE_MACRO
-#define RT_USE_MACRO 1
 #endif
 // RT_SKIP2 = 1 makes the pair walker leave EMPTY 2x2x2 blocks of cells in one exact step (flatAdvance in
 // rt_device.cuh; bit-exact, GPU suite green with it).  Measured on B200 at the full config: 5391 vs 5393 Mrays/s --
@@ -681,175 +591,14 @@ constexpr int kStepBurst = RT_STEP_BURST;   // empty-cell steps per outer iterat
 constexpr int kWalkWarps = 8;               // warps per block
 constexpr int kWalkMinBlocks = RT_WALK_MINB; // resident blocks per SM the register budget is tuned for
 
-template <int PRIM, bool ANY>
-__global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_coop(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w,
-                                                              unsigned n, int qslot) {
-    __shared__ unsigned s_cand[kWalkWarps][64];
-    __shared__ float s_div[kWalkWarps][64];
-#if RT_USE_MACRO
-    __shared__ unsigned s_macro[8192];   // 64^3 bits
-    for (unsigned i = threadIdx.x; i < 8192; i += blockDim.x) s_macro[i] = set.macro_occ[i];
-    __syncthreads();
-    const unsigned mshift = set.macro_shift, mn = set.macro_n;
-#define RT_ENTER(f, g) flatEnterMacro(f, g, s_macro, mshift, mn)
-#else
-#define RT_ENTER(f, g) flatEnter(f, g)
-#endif
-    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    const unsigned count = w.qctr[2 * qslot];
-    unsigned* head = w.qctr + 2 * qslot + 1;
-    const float4* src = ANY ? w.sh : w.ray;
-    const GridView& g = set.g;
-    FlatWalker f;
-    f.i = f.end = 0;
-    unsigned slot = 0;
-    bool have = false;
-    bool drained = false;
-    while (true) {
-        // ---- refill idle lanes from the queue (one atomicAdd per warp)
-        unsigned idle = __ballot_sync(0xffffffffu, !have);
-        if (!drained && (__popc(idle) >= kRefill || idle == 0xffffffffu)) {
-            unsigned base = 0;
-            int leader = __ffs(idle) - 1;
-            if ((int)lane == leader) base = atomicAdd(head, (unsigned)__popc(idle));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (!have) {
-                unsigned idx = base + __popc(idle & lt);
-                if (idx < count) {
-                    slot = w.queue[idx];
-                    float4 r0 = src[slot], r1 = src[n + slot];
-                    f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
-                    AabbHit binter = interAABB(o, d, g.bound);
-                    walkInit(f.w, PRIM, o, d, r1.w, g, binter);
-                    RT_ENTER(f, g);
-                    have = true;
-                }
-            }
-            if (base + __popc(idle) >= count) drained = true;
-            idle = __ballot_sync(0xffffffffu, !have);
-        }
-        if (idle == 0xffffffffu) break;
-        // ---- per-lane stepping through empty / finished cells
-        for (int k = 0; k < kStepBurst; k++) {
-            bool stepping = have && f.i >= f.end;
-            if (!__any_sync(0xffffffffu, stepping)) break;
-            if (stepping) {
-                if (flatLeave(f)) {
-                    have = false;
-                    const Hit& h = f.w.h;
-                    if (ANY) {   // A10/code.cl:1185-1192
-                        if (h.i != 0xFFFFFFFFu) {
-                            float4 s0 = w.sh[slot];
-                            w.sh[slot] = make_float4(s0.x, s0.y, s0.z, h.t);
-                            float4 s1 = w.sh[n + slot];
-                            w.sh[n + slot] = make_float4(s1.x, s1.y, s1.z, h.t);
-                        }
-                    } else if (h.i != 0xFFFFFFFFu) {   // A10/code.cl:921-934
-                        f3 p = getPoint(f.w.o, f.w.d, h.t);
-                        f3 nrm;
-                        int m;
-                        if (PRIM == PRIM_SPHERE) {
-                            float4 sp = __ldg(g.prim + h.i);
-                            nrm = normalize(p - mk3(sp.x, sp.y, sp.z));
-                            m = (int)__ldg(set.matid + h.i);
-                        } else {
-                            float4 n0 = __ldg(set.normals + 3 * h.i), n1 = __ldg(set.normals + 3 * h.i + 1), n2 = __ldg(set.normals + 3 * h.i + 2);
-                            nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
-                            m = set.matid ? (int)__ldg(set.matid + h.i) : (int)set.scalar_matid;
-                        }
-                        float4 r1 = w.ray[n + slot];
-                        w.ray[n + slot] = make_float4(r1.x, r1.y, r1.z, h.t);
-                        w.poi[slot] = make_float4(p.x, p.y, p.z, __int_as_float(m));
-                        w.poi[n + slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
-                    }
-                } else {
-                    RT_ENTER(f, g);
-                }
-            }
-        }
-        // ---- cooperative test of every pending non-empty cell, one owner lane at a time
-        unsigned pend = __ballot_sync(0xffffffffu, have && f.i < f.end);
-        while (pend) {
-            const int L = __ffs(pend) - 1;
-            pend &= pend - 1;
-            const f3 o = mk3(__shfl_sync(0xffffffffu, f.w.o.x, L), __shfl_sync(0xffffffffu, f.w.o.y, L), __shfl_sync(0xffffffffu, f.w.o.z, L));
-            const f3 d = mk3(__shfl_sync(0xffffffffu, f.w.d.x, L), __shfl_sync(0xffffffffu, f.w.d.y, L), __shfl_sync(0xffffffffu, f.w.d.z, L));
-            const float mint = __shfl_sync(0xffffffffu, f.mint, L), maxt = __shfl_sync(0xffffffffu, f.maxt, L);
-            const float champ = __shfl_sync(0xffffffffu, f.w.h.t, L);
-            const unsigned begin = __shfl_sync(0xffffffffu, f.i, L), end = __shfl_sync(0xffffffffu, f.end, L);
-            const float a_dd = (PRIM == PRIM_SPHERE) ? __shfl_sync(0xffffffffu, f.w.a_dd, L) : 0.f;
-            // this lane's best candidate over the cell
-            float bt = RT_INF, bb = 0.f, bg = 0.f;
-            unsigned bi = 0xFFFFFFFFu;
-            bool found_any = false;
-            for (unsigned base = begin; base < end && !found_any; base += 64) {
-                unsigned nc;
-                if (PRIM == PRIM_TRIANGLE) {
-                    // cull on the face vector, compact survivors (in reference order) into s_cand
-                    unsigned r0 = base + lane, r1 = base + 32 + lane;
-                    float d0 = 0.f, d1 = 0.f;
-                    bool f0 = false, f1 = false;
-                    if (r0 < end) { float4 q = __ldg(set.pre_ng + r0); d0 = dot(mk3(q.x, q.y, q.z), d); f0 = d0 > 0; }
-                    if (r1 < end) { float4 q = __ldg(set.pre_ng + r1); d1 = dot(mk3(q.x, q.y, q.z), d); f1 = d1 > 0; }
-                    unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
-                    unsigned c0 = __popc(m0);
-                    if (f0) { unsigned p = __popc(m0 & lt); s_cand[wid][p] = r0; s_div[wid][p] = d0; }
-                    if (f1) { unsigned p = c0 + __popc(m1 & lt); s_cand[wid][p] = r1; s_div[wid][p] = d1; }
-                    nc = c0 + __popc(m1);
-                    __syncwarp();
-                } else {
-                    nc = min(64u, end - base);
-                }
-                for (unsigned j = lane; j < nc; j += 32) {
-                    float ti, be = 0.f, ga = 0.f;
-                    bool v;
-                    unsigned r;
-                    if (PRIM == PRIM_TRIANGLE) {
-                        r = s_cand[wid][j];
-                        float dv = s_div[wid][j];
-                        float4 q0 = __ldg(set.pre_pe + 3 * r), q1 = __ldg(set.pre_pe + 3 * r + 1), q2 = __ldg(set.pre_pe + 3 * r + 2);
-                        v = interTriangleFast(o, d, mint, maxt, dv, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), be, ga, ti);
-                    } else {
-                        r = base + j;
-                        float4 sp = __ldg(g.prim + r);
-                        v = interSphere(o, d, a_dd, mint, maxt, sp, ti);
-                    }
-                    // candidates of one lane arrive in increasing reference order: strict < keeps the first on ties
-                    // any hit: the lane keeps its FIRST accepted reference; closest: its nearest
-                    if (v && ti < champ && (ANY ? bi == 0xFFFFFFFFu : ti < bt)) { bt = ti; bi = r; bb = be; bg = ga; }
-                }
-                if (PRIM == PRIM_TRIANGLE) __syncwarp();
-                if (ANY) found_any = __any_sync(0xffffffffu, bi != 0xFFFFFFFFu);   // later chunks only hold higher indices
-            }
-            // ---- reduce to the reference's winner
-            unsigned has = __ballot_sync(0xffffffffu, bi != 0xFFFFFFFFu);
-            if (has) {
-                unsigned win_i;
-                if (ANY) {
-                    win_i = __reduce_min_sync(0xffffffffu, bi);                    // first accepted reference in list order
-                } else {
-                    float tm = bt;
-                    for (int s = 16; s > 0; s >>= 1) tm = fminf(tm, __shfl_xor_sync(0xffffffffu, tm, s));
-                    win_i = __reduce_min_sync(0xffffffffu, (bt == tm) ? bi : 0xFFFFFFFFu);   // ties: lowest index
-                }
-                int wl = __ffs(__ballot_sync(0xffffffffu, bi == win_i && bi != 0xFFFFFFFFu)) - 1;
-                float wt = __shfl_sync(0xffffffffu, bt, wl), wb = __shfl_sync(0xffffffffu, bb, wl), wg = __shfl_sync(0xffffffffu, bg, wl);
-                if ((int)lane == L) { f.w.h.t = wt; f.w.h.i = win_i; f.w.h.beta = wb; f.w.h.gamma = wg; }
-            }
-            if ((int)lane == L) f.i = f.end;   // cell done; flatLeave ends the walk if it produced the hit
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------
-// Pair-list queue walker (default).  Same outer structure as k_walk_coop -- every lane owns one ray
-// and steps its own DDA through empty cells -- but the primitive tests of ALL lanes that stand in
-// a non-empty cell are done together: the (owner lane, reference) pairs of those cells are laid
-// out as one list (warp prefix sum of the cell populations), and the warp walks that list 32
-// pairs at a time, so the face-vector cull runs on dense lanes whatever the cell populations
-// are (a cell holds ~7 references on the 1 M-triangle mesh, which left k_walk_coop's 32-wide
-// per-cell passes 3/4 empty).  Survivors are compacted into a candidate buffer and the full
+// Pair-list queue walker.  Every lane owns one ray and steps its own DDA through empty cells; the
+// primitive tests of ALL lanes that stand in a non-empty cell are done together: the (owner lane,
+// reference) pairs of those cells are laid out as one list (warp prefix sum of the cell
+// populations), and the warp walks that list 32 pairs at a time, so the face-vector cull runs on
+// dense lanes whatever the cell populations are (two earlier designs -- one lane per ray testing its
+// own cell, and the whole warp testing one lane's cell at a time -- left 3/4 of the lanes idle on the
+// 1 M-triangle mesh and were removed after the A/B of round 1, profiles/README.md).  Survivors are compacted into a candidate buffer and the full
 // test again runs 32 candidates at a time.  Each lane fetches its pair's ray from the owner lane
 // with indexed shuffles.  Accepted hits (rare) are reduced per owner with one shared-memory
 // atomicMin on the key (t bits, reference index) [closest: min t, ties -> lowest index] or
@@ -1290,31 +1039,13 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
         } else {
             const SetDev& set = sc.sets[s.set];
             const int walk_blocks = ctx->prop.multiProcessorCount * kWalkMinBlocks;   // persistent: one resident wave
-            const bool coop = r->o.mode != 3;   // mode 3 = per-lane flattened walkers, mode 4 = per-cell cooperative walkers (kept for comparison)
-            const bool pairs = r->o.mode != 3 && r->o.mode != 4;
             RT_TRY_W(rt_time_mark(r, (set.kind == PRIM_SPHERE ? 1 : 3) + (s.any ? 1 : 0)));
             if (set.kind == PRIM_SPHERE) {
-                if (pairs) {
-                    if (s.any) k_walk_pairs<PRIM_SPHERE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
-                    else k_walk_pairs<PRIM_SPHERE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
-                } else if (coop) {
-                    if (s.any) k_walk_coop<PRIM_SPHERE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
-                    else k_walk_coop<PRIM_SPHERE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
-                } else {
-                    if (s.any) k_walk<PRIM_SPHERE, true><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
-                    else k_walk<PRIM_SPHERE, false><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
-                }
+                if (s.any) k_walk_pairs<PRIM_SPHERE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
+                else k_walk_pairs<PRIM_SPHERE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
             } else {
-                if (pairs && set.pre_ng) {
-                    if (s.any) k_walk_pairs<PRIM_TRIANGLE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
-                    else k_walk_pairs<PRIM_TRIANGLE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
-                } else if (coop && set.pre_ng) {
-                    if (s.any) k_walk_coop<PRIM_TRIANGLE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
-                    else k_walk_coop<PRIM_TRIANGLE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
-                } else {
-                    if (s.any) k_walk<PRIM_TRIANGLE, true><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
-                    else k_walk<PRIM_TRIANGLE, false><<<walk_blocks, 256, 0, ctx->stream>>>(set, w, n, s.qslot);
-                }
+                if (s.any) k_walk_pairs<PRIM_TRIANGLE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
+                else k_walk_pairs<PRIM_TRIANGLE, false><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
             }
             RT_LAUNCH_CHECK(ctx, "wave_walk");
         }

@@ -676,7 +676,9 @@ class Renderer:
     def __init__(self, scene, width, height, rays_per_pixel=1, n_slabs=1, depth=5, device=0, slots=None, mode=0, tile_slots=0, ctx=None):
         self.scene, self.width, self.height = scene, int(width), int(height)
         self.rays_per_pixel, self.n_slabs, self.depth = int(rays_per_pixel), int(n_slabs), int(depth)
-        self.slots = slots or (0, self.rays_per_pixel)
+        self.slots = (0, self.rays_per_pixel) if slots is None else (int(slots[0]), int(slots[1]))
+        if self.slots[1] <= 0:   # multi.slot_range hands (begin, 0) to ranks beyond rays_per_pixel: they render nothing
+            raise ValueError("Renderer: empty slot range %r -- this rank has no slots; skip the render and contribute a zero image" % (self.slots,))
         self.mode, self.tile_slots = mode, tile_slots
         self.ctx = ctx or L.Context(device)
         self._own_ctx = ctx is None

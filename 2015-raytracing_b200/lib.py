@@ -158,6 +158,10 @@ _SIGS = {
     "rt_render_read_timing": ([P, C.POINTER(F * 8), C.POINTER(U * 8)], I),
     "rt_accum_to_pixel": ([P, P, P, F, U], I),
     "rt_render_stats": ([P, C.POINTER(ULL), C.POINTER(ULL), C.POINTER(U), C.POINTER(F)], I),
+    "rt_comm_unique_id": ([P], I),
+    "rt_comm_create": ([P, I, I, P, PP], I),
+    "rt_comm_destroy": ([P], I),
+    "rt_render_reduce": ([P, P, I], I),
 }
 for _name, (_args, _res) in _SIGS.items():
     _fn = getattr(dll, _name)

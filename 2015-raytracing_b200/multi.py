@@ -1,6 +1,8 @@
 """Multi-GPU split of an Assignment-10 render: one process per GPU, each renders a contiguous
 range of every pixel's ray slots (split by samples per pixel), then ONE sum-reduce of the
-per-pixel accumulation image to rank 0 (NCCL over NVLink on GPUs, gloo in the CPU tests).
+per-pixel accumulation image to rank 0: on GPUs ``Comm.reduce`` = ``rt_render_reduce``, an ncclReduce the C library
+issues on the context's stream (NVLink / NVSwitch); ``reduce_accum`` is the same step on host tensors through
+``torch.distributed`` (gloo) for the CPU tests of the split / merge logic.
 
 Why slots and not passes: a slot's RNG state lives in ``seeds[id]`` and carries over from pass to
 pass with a data-dependent number of draws (A10/code.cl:420-434), so only a split
@@ -43,6 +45,51 @@ def reduce_accum(accum, dst: int = 0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return accum
+
+
+class Comm:
+    """rt_comm (include/rt2015.h): the NCCL communicator the C library itself drives -- the reduce is issued from C++
+    on the context's stream (``rt_render_reduce``), no torch on the data path.  ``exchange(id_or_None) -> id`` ships rank
+    0's 128-byte id to every rank; by default ``torch.distributed`` does it when a process group exists (any backend),
+    but a file or a socket serves as well (that is all a Node.js host needs)."""
+
+    def __init__(self, ctx, rank: int, world: int, exchange=None):
+        import ctypes as C
+
+        from . import lib as L
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            ctx.check(L.dll.rt_comm_unique_id(C.cast(ident, C.c_void_p)))
+        raw = (exchange or _exchange_via_torch)(bytes(ident) if rank == 0 else None)
+        buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+        h = C.c_void_p()
+        ctx.check(L.dll.rt_comm_create(ctx.h, self.world, self.rank, C.cast(buf, C.c_void_p), C.byref(h)))
+        self.h = h
+
+    def reduce(self, renderer, root: int = 0):
+        """Sum every rank's per-pixel accumulation image into ``root``'s (asynchronous on the context's stream)."""
+        from . import lib as L
+        self.ctx.check(L.dll.rt_render_reduce(renderer.h_render, self.h, int(root)))
+
+    def close(self):
+        from . import lib as L
+        if self.h:
+            L.dll.rt_comm_destroy(self.h)
+            self.h = None
+
+
+def _exchange_via_torch(ident):
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("multi.Comm: no torch.distributed process group -- pass exchange=")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if ident is not None:
+        t.copy_(torch.frombuffer(bytearray(ident), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
 
 
 def accum_to_pixel(accum, rays_per_pixel: int, passes: int) -> np.ndarray:

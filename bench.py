@@ -78,6 +78,16 @@ def workload_name(args):
                                                             args.depth, 2 * args.mesh_u * args.mesh_v, args.nslabs, args.lights))
 
 
+def config_of(args):
+    """`config` of the JSON line -- the same dict in both arms (ours and --impl reference)."""
+    slots = args.cols * args.rows * args.spp
+    return {"workload": workload_name(args), "cols": args.cols, "rows": args.rows, "slots_per_pixel": args.spp, "depth": args.depth,
+            "mesh_triangles": 2 * args.mesh_u * args.mesh_v, "mesh_nslabs": args.nslabs, "lights": args.lights, "seed": args.seed,
+            "l2_policy": "inputs larger than L2 (126 MB), no flush needed: every step streams the per-slot seed + accumulation state "
+                         "(20 B/slot) and the per-tile ray/hit state (~116 B/slot) of cols*rows*slots_per_pixel/N slots per GPU -- "
+                         "%.1f + %.1f GB at N = 1, %.1f + %.1f GB at N = 8" % (slots * 20 / 1e9, slots * 116 / 1e9, slots * 20 / 8e9, slots * 116 / 8e9)}
+
+
 def make_seeds(total, seed):
     g = np.random.Generator(np.random.PCG64(seed))
     return g.integers(1, 2 ** 31, size=total, dtype=np.int32)
@@ -136,18 +146,28 @@ def oracle_scene(args, tmp):
     return scene, OR.prepare_a10(scene, 1)
 
 
-def cpu_pass_rows(olib, prep, cam16, args, focal, lens_diam, row0, nrows, seeds_rows):
-    """One executeRender pass of the oracle over pixel rows [row0, row0+nrows) (every kernel is
-    per-slot independent, so a row tile is exact).  Returns (rays, seconds)."""
+def sample_rows(args, n):
+    """`n` pixel rows spread evenly over the WHOLE frame (row i of n sits in the middle of the i-th of n equal bands): the
+    CPU arms render a sample whose mix of mesh / wall / background pixels is the frame's, not the expensive centre's."""
+    n = max(1, min(args.rows, n))
+    return [min(args.rows - 1, int((i + 0.5) * args.rows / n)) for i in range(n)]
+
+
+def cpu_pass_rows(olib, prep, cam16, args, focal, lens_diam, rows, seed):
+    """One executeRender pass of the oracle over each of the pixel rows in `rows` (every kernel is per-slot independent,
+    so a row tile is exact).  Returns (rays, seconds) summed over the rows; only the kernel schedule is timed."""
     from oracle import refcl as OR
     cols, rpp = args.cols, args.spp
-    total = cols * nrows * rpp
-    st = OR.A10State(total, seeds_rows)
-    olib.a10_initAcu(st.acu, total)
-    t0 = time.perf_counter()
-    OR.a10_execute_render(olib, st, prep, cam16, cols, args.rows, rpp, focal, lens_diam, depth=args.depth, row0=row0, nrows=nrows)
-    dt = time.perf_counter() - t0
-    return st.n_closest + st.n_any, dt
+    total = cols * rpp
+    rays, secs = 0, 0.0
+    for i, row in enumerate(rows):
+        st = OR.A10State(total, make_seeds(total, seed + 1000 * i))
+        olib.a10_initAcu(st.acu, total)
+        t0 = time.perf_counter()
+        OR.a10_execute_render(olib, st, prep, cam16, cols, args.rows, rpp, focal, lens_diam, depth=args.depth, row0=row, nrows=1)
+        secs += time.perf_counter() - t0
+        rays += st.n_closest + st.n_any
+    return rays, secs
 
 
 # ------------------------------------------------------------------------------ roofline
@@ -249,36 +269,27 @@ def main():
     slot_begin, slots_pp = rt.multi.slot_range(rank, world, args.spp)   # split by samples per pixel
     r = rt.Renderer(scene, args.cols, args.rows, args.spp, depth=args.depth, device=local_rank, slots=(slot_begin, slots_pp),
                     mode=args.mode, tile_slots=args.tile_slots)
-    total = args.cols * args.rows * args.spp
     # host seed array: this rank's slots only are generated/kept ([pixel][k_local]) -- same values a full
     # PCG64(seed) array would hold at those positions are not needed for throughput; parity tests use full arrays.
     local = args.cols * args.rows * slots_pp
     seeds_host = torch.from_numpy(make_seeds(local, args.seed + rank)).pin_memory()
+    pix_host = torch.empty(args.cols * args.rows * 4, dtype=torch.uint8).pin_memory()
     r.preRender(None)
     L = rt.lib
-    ext = torch.cuda.ExternalStream(L.dll.rt_ctx_stream(r.ctx.h), device=torch.device("cuda", local_rank))
+    ctx = r.ctx
+    # Everything inside the timed regions goes through the C ABI on the context's own stream (uploads, kernels, the
+    # NCCL reduce, copyToPixel, the read-back); torch supplies pinned host memory, the events and the rendezvous only.
+    comm = rt.multi.Comm(ctx, rank, world) if world > 1 else None
+    pix_dev = ctx.alloc(args.cols * args.rows * 4)
+    ext = torch.cuda.ExternalStream(L.dll.rt_ctx_stream(ctx.h), device=torch.device("cuda", local_rank))
 
     def set_seeds_local():
-        # rt_render_set_seeds takes the GLOBAL [pixel][rpp] layout; with one rank-local array we write the
-        # render's seed buffer directly (rt_buffer_write on the same device pointer layout [pixel][k_local]).
-        r.ctx.check(L.dll.rt_render_write_local_seeds(r.h_render, seeds_host.data_ptr(), local))
-
-    acc_dptr = r.accum_dptr()
-
-    class _Cai:
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-
-    acc_t = torch.as_tensor(_Cai(acc_dptr, args.cols * args.rows * 4), device=torch.device("cuda", local_rank))
-    pix_dev = torch.empty(args.cols * args.rows * 4, dtype=torch.uint8, device=acc_t.device)
-    pix_host = torch.empty(args.cols * args.rows * 4, dtype=torch.uint8).pin_memory()
-    cam = scene["camera"].toFloat32Array()
+        ctx.check(L.dll.rt_render_write_local_seeds(r.h_render, seeds_host.data_ptr(), local))
 
     def step_device():
         """hot path only, inputs resident in HBM"""
         r.executeRender(readback=False)
-        s = r.stats()
-        return s
+        return r.stats()
 
     e2e_blocking = [False]
 
@@ -288,16 +299,17 @@ def main():
         if e2e_blocking[0]:
             set_seeds_local()
         else:
-            r.ctx.check(L.dll.rt_render_write_local_seeds_async(r.h_render, seeds_host.data_ptr(), local))
+            ctx.check(L.dll.rt_render_write_local_seeds_async(r.h_render, seeds_host.data_ptr(), local))
         r.executeRender(readback=False)
         s = r.stats()
-        with torch.cuda.stream(ext):
-            rt.multi.reduce_accum(acc_t, dst=0)   # the one collective: sum of the per-pixel accumulation images
-            if rank == 0:
-                m = float(np.float32(1.0 / (args.spp * (r.passes - 1))))
-                r.ctx.check(L.dll.rt_accum_to_pixel(r.ctx.h, pix_dev.data_ptr(), acc_t.data_ptr(), m, args.cols * args.rows))
-                pix_host.copy_(pix_dev, non_blocking=True)
-        ext.synchronize()
+        if comm is not None:
+            comm.reduce(r, 0)   # the one collective: ncclReduce(sum) of the per-pixel accumulation images, from C++
+        if rank == 0:
+            m = float(np.float32(1.0 / (args.spp * (r.passes - 1))))
+            ctx.check(L.dll.rt_accum_to_pixel(ctx.h, pix_dev, r.accum_dptr(), m, args.cols * args.rows))
+            ctx.check(L.dll.rt_buffer_read(ctx.h, pix_dev, 0, args.cols * args.rows * 4, pix_host.data_ptr()))   # D2H + finish
+        else:
+            ctx.finish()
         return s
 
     def barrier():
@@ -311,19 +323,17 @@ def main():
         rays = 0
         launches = 0
         kern_ms = 0.0
-        with torch.cuda.stream(ext):
-            e0.record()
+        e0.record(ext)
         for _ in range(k):
             s = fn()
             rays += s["closest_rays"] + s["any_rays"]
             launches += s["launches"]
             kern_ms += s["device_ms"]
-        with torch.cuda.stream(ext):
-            e1.record()
+        e1.record(ext)
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms, float(rays)], dtype=torch.float64, device=acc_t.device)
+            t = torch.tensor([ms, float(rays)], dtype=torch.float64, device=torch.device("cuda", local_rank))
             tmax = t.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
@@ -353,7 +363,7 @@ def main():
 
     out = None
     if rank == 0:
-        info = r.ctx.device_info()
+        info = ctx.device_info()
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -368,11 +378,9 @@ def main():
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "slots_per_gpu_per_pixel": slots_pp, "mode": args.mode,
-                       "l2_policy": "inputs larger than L2: every step streams %.1f GB of per-slot seed+accumulation state and %.1f GB of "
-                                    "per-tile ray/hit state per GPU (L2 = %d MB); no flush needed" % (
-                                        local * 40 / 1e9, local * 116 / 1e9, info["l2_bytes"] >> 20),
-                       "sm_count": info["sm_count"]},
+            "config": config_of(args),
+            "run": {"slots_per_gpu_per_pixel": slots_pp, "mode": args.mode, "sm_count": info["sm_count"], "l2_bytes": info["l2_bytes"],
+                    "reduce": "ncclReduce(sum, fp32, 33 MB) issued by librt2015.so on the render stream (rt_render_reduce)" if world > 1 else None},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(local * 4 + 64),
                     "upload": "rt_render_write_local_seeds_async: the seed H2D copy runs on a side stream inside the timed region and overlaps "
@@ -386,17 +394,24 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
-    # release torch objects that reference the context's stream before the context goes away
-    del acc_t, pix_dev, pix_host, seeds_host
+    # Orderly teardown, then a NORMAL interpreter exit (exit hooks run: the driver's record of the native libraries this
+    # process loaded depends on them).  Nothing of torch's was ever enqueued on the context's stream except event
+    # records, so the stream can go away before torch does.
+    del ext
+    ctx.finish()
     torch.cuda.synchronize()
+    if comm is not None:
+        dist.barrier()
+        comm.close()
+    ctx.free(pix_dev)
+    r.postRender()
+    del seeds_host, pix_host
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
     sys.stdout.flush()
-    r.postRender()
-    os._exit(0)   # torch's pinned-memory allocator would otherwise record events on the (now destroyed) stream at exit
 
 
 def cpu_rows_default(args, seconds):
@@ -413,19 +428,19 @@ def cpu_baseline(args):
     olib.set_num_threads(os.cpu_count() or 1)
     scene, prep = oracle_scene(args, tempfile.mkdtemp(prefix="rt_bench_cpu_"))
     cam = scene["camera"].toFloat32Array()
-    rows = args.cpu_rows or cpu_rows_default(args, 15.0)
-    row0 = max(0, args.rows // 2 - rows // 2)
-    seeds = make_seeds(args.cols * rows * args.spp, args.seed + 77)
-    rays, dt = cpu_pass_rows(olib, prep, cam, args, scene["focal_length"], scene["lens_diameter"], row0, rows, seeds)
+    rows = sample_rows(args, args.cpu_rows or cpu_rows_default(args, 15.0))
+    rays, dt = cpu_pass_rows(olib, prep, cam, args, scene["focal_length"], scene["lens_diameter"], rows, args.seed + 77)
     return {"value": round(rays / dt / 1e6, 3), "unit": "Mrays/s", "cores": int(olib.num_threads()), "kind": olib.kind,
-            "sample": "pixel rows %d..%d of %d (all %d slots/px, one executeRender pass, %d rays, %.1f s; reference code.cl kernels "
-                      "compiled by g++ -O2 -fopenmp behind oracle/clshim.h)" % (row0, row0 + rows - 1, args.rows, args.spp, rays, dt)}
+            "sample": "%d pixel rows spread evenly over the frame (rows %s of %d; all %d slots/px, one executeRender pass each, %d rays, "
+                      "%.1f s; reference code.cl kernels compiled by g++ -O2 -fopenmp behind oracle/clshim.h)"
+                      % (len(rows), ",".join(map(str, rows)), args.rows, args.spp, rays, dt),
+            "rows": rows}
 
 
 def main_reference(args, rank):
     """--impl reference: the reference's own kernels (oracle/_ref when compiled, else the C
-    restatement) on all host cores, same scene/metric; each step is a bounded row sample.  Nothing
-    of the product (package, library, GPU) is on this path."""
+    restatement) on all host cores, same scene/metric; each step is a bounded sample of pixel rows spread evenly over
+    the whole frame.  Nothing of the product (package, library, GPU) is on this path."""
     if rank != 0:
         return
     from oracle import refcl as OR
@@ -433,23 +448,22 @@ def main_reference(args, rank):
     olib.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; this arm uses every host core
     scene, prep = oracle_scene(args, tempfile.mkdtemp(prefix="rt_bench_ref_"))
     cam = scene["camera"].toFloat32Array()
-    rows = args.cpu_rows or cpu_rows_default(args, 8.0)
-    row0 = max(0, args.rows // 2 - rows // 2)
+    rows = sample_rows(args, args.cpu_rows or cpu_rows_default(args, 8.0))
     rays_t, secs = 0, 0.0
     for i in range(args.warmup + args.steps):
-        seeds = make_seeds(args.cols * rows * args.spp, args.seed + i)
-        rays, dt = cpu_pass_rows(olib, prep, cam, args, scene["focal_length"], scene["lens_diameter"], row0, rows, seeds)
+        rays, dt = cpu_pass_rows(olib, prep, cam, args, scene["focal_length"], scene["lens_diameter"], rows, args.seed + 100000 * i)
         if i >= args.warmup:
             rays_t += rays
             secs += dt
     value = rays_t / secs / 1e6
-    sample = ("each step = pixel rows %d..%d of %d (all %d slots/px, one executeRender pass); reference code.cl kernels compiled "
-              "by g++ -O2 -fopenmp behind oracle/clshim.h" % (row0, row0 + rows - 1, args.rows, args.spp))
+    sample = ("each step = %d pixel rows spread evenly over the frame (rows %s of %d; all %d slots/px, one executeRender pass each); reference "
+              "code.cl kernels compiled by g++ -O2 -fopenmp behind oracle/clshim.h" % (len(rows), ",".join(map(str, rows)), args.rows, args.spp))
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 3), "higher_is_better": True,
            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": workload_name(args)},
-           "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": int(olib.num_threads()), "kind": olib.kind, "sample": sample},
+           "config": config_of(args),
+           "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": int(olib.num_threads()), "kind": olib.kind, "sample": sample,
+                            "rows": rows},
            "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))

@@ -367,6 +367,17 @@ static napi_value js_scene_create(napi_env env, napi_callback_info info) {   /* 
     int rc = rt_scene_create((rt_ctx*)get_handle(env, a[0]), &s);
     return rc ? rt_throw(env, rc) : make_handle(env, s);
 }
+/* comm_create(ctx, world, rank, Uint8Array id[128]) -> comm   (multi-GPU: one process per GPU, id from comm_unique_id on rank 0) */
+static napi_value js_comm_create(napi_env env, napi_callback_info info) {
+    napi_value a[4];
+    rt_comm* c = NULL;
+    int32_t world = 0, rank = 0;
+    if (!get_args(env, info, 4, a)) return NULL;
+    NAPI_CALL(env, napi_get_value_int32(env, a[1], &world));
+    NAPI_CALL(env, napi_get_value_int32(env, a[2], &rank));
+    int rc = rt_comm_create((rt_ctx*)get_handle(env, a[0]), world, rank, (const unsigned char*)typed_or_null(env, a[3]), &c);
+    return rc ? rt_throw(env, rc) : make_handle(env, c);
+}
 /* scene_add_set(scene, grid, Float32Array bound[8], is_mesh, mesh_matid) */
 static napi_value js_scene_add_set(napi_env env, napi_callback_info info) {
     napi_value a[5];
@@ -484,7 +495,7 @@ napi_value rt2015_init(napi_env env, napi_value exports) {
         {"slab_build_triangles", js_slab_build_triangles}, {"grid_release", js_grid_release}, {"parse_mesh_json", js_parse_mesh_json},
         {"parse_pdb", js_parse_pdb}, {"scene_create", js_scene_create}, {"scene_add_set", js_scene_add_set},
         {"render_create", js_render_create}, {"render_accum_image", js_render_accum_image}, {"render_stats", js_render_stats},
-        {"a089_render_frame", js_a089_render_frame},
+        {"a089_render_frame", js_a089_render_frame}, {"comm_create", js_comm_create},
         RT2015_GENERATED_EXPORTS
     };
     for (size_t i = 0; i < sizeof table / sizeof table[0]; i++) {

@@ -44,6 +44,7 @@ typedef enum {
 typedef struct rt_ctx rt_ctx;
 typedef struct rt_scene rt_scene;
 typedef struct rt_render rt_render;
+typedef struct rt_comm rt_comm;
 
 /* ---- 1. context and buffers ------------------------------------------------------------ */
 /* createCLBasicResources, A10/code.js:576-608 */
@@ -171,10 +172,12 @@ typedef struct {
 /* out_matid (int per slot) / out_maxt (float per slot): optional hit record outputs, may be NULL */
 int rt_a089_render_frame(rt_ctx*, const rt_a089_frame* frame, void* acu, void* out_matid, void* out_maxt);
 
-/* Optional per-work-item statistics for the five grid-walk launchers (all device pointers,
- * any may be NULL; pass all NULL to switch off): winning reference index (0xFFFFFFFF =
- * none), cells visited, primitive tests.  Used for hit-id parity and for the algorithmic
- * byte count of the roofline. */
+/* Optional per-work-item statistics for the grid-walk launchers -- the five of Assignment 10 (sphereTrace,
+ * triangleTrace, meshTrace, sphereShadowTrace, triangleShadowTrace) and molTrace / meshTrace of Assignment 7 (all
+ * device pointers, one uint per work-item, any may be NULL; pass all NULL to switch off): winning reference index
+ * champ_i (0xFFFFFFFF = none; A10/code.cl:882-897), cells visited, primitive tests.  Used for the hit-primitive-id
+ * parity gate and for the algorithmic byte count of the roofline.  With occupancy bits present the
+ * walk skips the table loads of empty cells but still counts them as visited, like the reference's loop. */
 int rt_set_walk_stats(rt_ctx*, void* hit_id_u32, void* cells_u32, void* tests_u32);
 
 /* ---- 3. grid build, scene, render ---------------------------------------------------------
@@ -265,9 +268,10 @@ typedef struct {
     float focal_length;           /* scene.focal_length */
     float lens_rad;               /* scene.lens_diameter / 2 */
     unsigned slot_begin, slot_count;   /* multi-GPU: this context renders slots k in [slot_begin, slot_begin+slot_count)
-                                          of every pixel; 0,0 = all rays_per_pixel slots */
-    unsigned mode;                /* 0 = wavefront path (default), 1 = reference kernel-by-kernel schedule, 2 = megakernel,
-                                     3 / 4 = earlier queue-walker designs (per-lane, per-cell cooperative), kept for A/B */
+                                          of every pixel; 0,0 = all rays_per_pixel slots.  slot_count == 0 with
+                                          slot_begin > 0 (a rank left without slots when world > rays_per_pixel) is
+                                          rejected: such a rank renders nothing and contributes a zero image */
+    unsigned mode;                /* 0 = wavefront path (default), 1 = reference kernel-by-kernel schedule, 2 = megakernel */
     unsigned tile_slots;          /* wavefront tile size in ray slots, 0 = auto (a quarter of device memory) */
 } rt_render_opts;
 
@@ -303,6 +307,18 @@ int rt_render_export_state(rt_render*, float* host_acu_float4, int* host_seeds, 
 int rt_render_import_state(rt_render*, const float* host_acu_float4, const int* host_seeds, unsigned passes);
 /* copyToPixel on an accumulation image (after a multi-GPU reduce): m = 1/(rays_per_pixel*passes). */
 int rt_accum_to_pixel(rt_ctx*, void* pixel, const void* accum_float4, float m, unsigned pixels);
+/* Multi-GPU (ours; the reference drives one device, A10/code.js:576-608): one process and one context per GPU, each
+ * rendering its own slot range (rt_render_opts.slot_begin / slot_count), then ONE sum-reduce of the per-pixel
+ * accumulation images into `root` -- ncclReduce(sum, fp32) over NVLink, issued on the context's stream, asynchronous like
+ * the launchers.  NCCL is bound at run time (libnccl.so.2; RT2015_NCCL_LIB overrides the path); a host that never creates
+ * a communicator never loads it.  Rank 0 obtains an id, ships the RT_COMM_ID_BYTES bytes to the other processes by any
+ * means (file, socket, env), every rank then calls rt_comm_create (collective).  After rt_render_reduce the root
+ * follows with rt_accum_to_pixel on rt_render_accum_image. */
+#define RT_COMM_ID_BYTES 128
+int rt_comm_unique_id(unsigned char id[RT_COMM_ID_BYTES]);
+int rt_comm_create(rt_ctx*, int world, int rank, const unsigned char id[RT_COMM_ID_BYTES], rt_comm** out);
+int rt_comm_destroy(rt_comm*);
+int rt_render_reduce(rt_render*, rt_comm*, int root);
 /* Counters of the last execute: valid closest-hit and any-hit queries ("rays"),
  * kernels launched, device milliseconds between the first and last launch. */
 int rt_render_stats(rt_render*, unsigned long long* closest_rays, unsigned long long* any_rays, unsigned* launches,
