@@ -31,35 +31,46 @@ thread_local unsigned int ref_tl_hit;
 #define REF_HOOK_HIT(i)
 #endif
 
+// The kernel text: _ref/aNN_code.inc, or -- instrumented build -- _ref/instr/_ref/aNN_code.inc with the hook macros.
+// (A quoted #include "_ref/..." would find the un-hooked file next to this source before any -I directory: round 1's
+// "instrumented" library was built that way and never counted anything.)
+#define REF_STR2(x) #x
+#define REF_STR(x) REF_STR2(x)
+#ifdef REF_INSTRUMENT
+#define REF_CODE(n) REF_STR(_ref/instr/_ref/n##_code.inc)
+#else
+#define REF_CODE(n) REF_STR(_ref/n##_code.inc)
+#endif
+
 namespace a01 {
-#include "_ref/a01_code.inc"
+#include REF_CODE(a01)
 }
 namespace a02 {
-#include "_ref/a02_code.inc"
+#include REF_CODE(a02)
 }
 namespace a03 {
-#include "_ref/a03_code.inc"
+#include REF_CODE(a03)
 }
 namespace a04 {
-#include "_ref/a04_code.inc"
+#include REF_CODE(a04)
 }
 namespace a05 {
-#include "_ref/a05_code.inc"
+#include REF_CODE(a05)
 }
 namespace a06 {
-#include "_ref/a06_code.inc"
+#include REF_CODE(a06)
 }
 namespace a07 {
-#include "_ref/a07_code.inc"
+#include REF_CODE(a07)
 }
 namespace a08 {
-#include "_ref/a08_code.inc"
+#include REF_CODE(a08)
 }
 namespace a09 {
-#include "_ref/a09_code.inc"
+#include REF_CODE(a09)
 }
 namespace a10 {
-#include "_ref/a10_code.inc"
+#include REF_CODE(a10)
 }
 
 static_assert(sizeof(a10::Ray) == 48 && sizeof(a10::Poi) == 64, "A10 layouts (SURVEY 8)");

@@ -162,6 +162,47 @@ def test_instrumented_build_is_arithmetic_neutral(tmp_path):
         assert np.array_equal(a, b)
 
 
+def test_instrumented_build_counts(tmp_path):
+    """The hooks of libref_instr.so really fire (round 1 shipped an "instrumented" library that had been compiled from the
+    un-hooked text and counted nothing): per pixel of an A07 meshTrace the winner champ_i is recorded exactly where the ray's
+    maxt was lowered, every started walk visits at least one cell, tests only happen in visited cells, and the un-instrumented
+    build leaves the sinks untouched."""
+    if not OR.have_reference():
+        pytest.skip("oracle/_ref not built")
+    fx = G.load("tri_teapot")
+    P = fx["params"]
+    m = G.meshes_of(fx)[0]
+    path = tmp_path / "m.json"
+    path.write_text(G.mesh_json_text(m["positions"], m["normals"], m["materialIndices"], m["materials"]))
+    md = OH.parseMeshJSON(str(path))
+    cols, rows, n = P["cols"], P["rows"], 10
+    out = {}
+    for instr in (True, False):
+        lib = OR.load_reference(instrumented=instr)
+        hit = np.full(cols * rows, 7, np.uint32)
+        cells, tests = np.full(cols * rows, 7, np.uint64), np.full(cols * rows, 7, np.uint64)
+        lib.set_stats(hit, cells, tests)
+        try:
+            _, rays, prep = OR.a07_render(lib, cols, rows, n, meshData=md)
+        finally:
+            lib.set_stats(None, None, None)
+        out[instr] = (hit, cells, tests, rays["maxt"].copy())
+    hit, cells, tests, maxt = out[True]
+    refs = int(prep["mesh"]["box"][-1])
+    got = hit != 0xFFFFFFFF
+    assert got.sum() > 100 and hit[got].max() < refs
+    # a hit lowers maxt below the exit parameter initTrace stored; recompute initTrace to compare
+    lib = OR.load_reference()
+    pix0, rays0 = np.zeros((rows * cols, 4), np.uint8), np.zeros(rows * cols, dtype=OR.RAY)
+    lib.a07_initTrace(pix0, prep["cam"], rays0, prep["aabb"], cols, rows)
+    assert np.array_equal(got, maxt != rays0["maxt"])
+    alive = rays0["mint"] != rays0["maxt"]
+    assert np.array_equal(cells > 0, alive) or (cells[alive] > 0).all() and not cells[~alive].any()
+    assert (tests[cells == 0] == 0).all() and tests.sum() > cells.sum() / 50 and tests[got].min() >= 1
+    assert np.array_equal(out[False][3].view(np.uint32), maxt.view(np.uint32))
+    assert (out[False][1] == 0).all() and (out[False][2] == 0).all() and (out[False][0] == 0xFFFFFFFF).all()
+
+
 @pytest.mark.parametrize("name", G.names("a10_"))
 def test_port_equals_reference_kernels(tmp_path, name):
     """The plain-C restatement of the Assignment-10 kernels (oracle/rt_oracle.c, kind "port") against the fixtures
