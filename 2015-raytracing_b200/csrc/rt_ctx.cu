@@ -133,4 +133,10 @@ int rt_set_walk_stats(rt_ctx* ctx, void* hit_id_u32, void* cells_u32, void* test
     return RT_OK;
 }
 
+int rt_set_walk_totals(rt_ctx* ctx, void* totals_u64x8) {
+    RT_CHECK_CTX(ctx);
+    ctx->st_totals = (unsigned long long*)totals_u64x8;
+    return RT_OK;
+}
+
 }  // extern "C"

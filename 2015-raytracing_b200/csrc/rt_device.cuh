@@ -194,6 +194,35 @@ RT_DEV RayR makeRay(f3 ori, f3 dst) {
     return r;
 }
 
+// Read-only loads of the scene data the queue walkers come back to all the time (cell table, occupancy bits, face
+// vectors).  RT_KEEP_L2 = 1 gives them an L2 evict-last policy (createpolicy + ld.global.nc.L2::cache_hint) so that the
+// gigabytes of per-slot state streaming through the same L2 do not push them out.
+#ifndef RT_KEEP_L2
+#define RT_KEEP_L2 0
+#endif
+RT_DEV float4 ldKeep(const float4* p) {
+#if RT_KEEP_L2
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+RT_DEV unsigned ldKeep(const unsigned* p) {
+#if RT_KEEP_L2
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    unsigned v;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------
 // Intersections
 // ---------------------------------------------------------------------------------------
@@ -398,9 +427,24 @@ struct Hit {
     int cx, cy, cz;   // champ_slab (A07 debug colouring)
 };
 
-struct WalkStats { unsigned long long cells, tests; };
+struct WalkStats { unsigned long long cells, tests, front; };   // front: triangle tests that pass the face cull (div > 0) and run the full test
 
 enum PrimKind { PRIM_SPHERE = 0, PRIM_TRIANGLE = 1 };
+
+// Optional statistics sinks of the grid-walk launchers (rt_set_walk_stats / rt_set_walk_totals): per work-item
+// champ_i / cells / tests, and launch-spanning totals {alive rays, walks started, cells, tests, hits, front-facing tests}.
+struct StatPtrs { unsigned* hit; unsigned* cells; unsigned* tests; unsigned long long* totals; };
+RT_DEV void tallyWalk(unsigned long long* t, unsigned walked, const WalkStats& ws, bool hit) {
+    if (!t) return;
+    const unsigned m = __activemask();   // the lanes that reached this point together
+    const bool lead = (int)(threadIdx.x & 31) == __ffs(m) - 1;
+    const unsigned v[6] = {1u, walked, (unsigned)ws.cells, (unsigned)ws.tests, hit ? 1u : 0u, (unsigned)ws.front};
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+        const unsigned r = __reduce_add_sync(m, v[q]);
+        if (lead && r) atomicAdd(t + q, (unsigned long long)r);
+    }
+}
 
 // One axis of the DDA preparation, A10/code.cl:696-707.
 struct Axis {
@@ -478,7 +522,14 @@ RT_DEV bool walkCell(Walker& w, const GridView& g, WalkStats* st) {
             v = interTriangle<TRI_INCL>(w.o, w.d, mint, maxt, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z),
                                         mk3(q2.x, q2.y, q2.z), be, ga, ti);
         }
-        if (STATS) st->tests++;
+        if (STATS) {
+            st->tests++;
+            if (PRIM == PRIM_TRIANGLE) {   // instrumentation only: the reference's first rejection (A10/code.cl:257-261)
+                float4 a0 = __ldg(g.prim + 3 * i), a1 = __ldg(g.prim + 3 * i + 1), a2 = __ldg(g.prim + 3 * i + 2);
+                f3 c0 = mk3(a0.x, a0.y, a0.z);
+                if (dot(cross(mk3(a2.x, a2.y, a2.z) - c0, mk3(a1.x, a1.y, a1.z) - c0), w.d) > 0) st->front++;
+            }
+        }
         if (v && ti < w.h.t) {
             w.h.t = ti;
             w.h.i = i;
@@ -561,9 +612,9 @@ RT_DEV void flatEnterMacro(FlatWalker& f, const GridView& g, const unsigned* s_m
         asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(b1) : "l"(g.box + cell + 1));
         if ((ow >> (cell & 31)) & 1u) { begin = b0; end = b1; }
 #else
-        if ((__ldg(g.occ + (cell >> 5)) >> (cell & 31)) & 1u) {
-            begin = __ldg(g.box + cell);
-            end = __ldg(g.box + cell + 1);
+        if ((ldKeep(g.occ + (cell >> 5)) >> (cell & 31)) & 1u) {
+            begin = ldKeep(g.box + cell);
+            end = ldKeep(g.box + cell + 1);
         }
 #endif
     }
@@ -766,14 +817,14 @@ RT_DEV Hit singleCellWalk(f3 o, f3 d, float maxt_in, const GridView& g, const fl
                 h.gamma = ga;
                 h.cx = h.cy = h.cz = 0;
                 if (ANY) {
-                    if (STATS) st->tests += j + 1;   // the reference's loop broke here
+                    if (STATS) { st->tests += j + 1; st->front += __popc(m1 & (0xFFFFFFFFu >> (31 - j))); }   // the reference's loop broke here
                     stop = true;
                     break;
                 }
             }
         }
         if (stop) break;
-        if (STATS) st->tests += cnt;
+        if (STATS) { st->tests += cnt; st->front += __popc(m1); }
     }
     }
     return h;

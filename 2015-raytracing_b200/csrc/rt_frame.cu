@@ -343,11 +343,15 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     r->pixels = (size_t)r->o.cols * r->o.rows;
     r->local_slots = r->pixels * r->slots_pp;
     if ((unsigned long long)r->pixels * r->o.rays_per_pixel > 0xFFFFFFFFull) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: total_rays exceeds the reference's uint range"); }
-    // default tile: as many slots as a quarter of the device memory holds (116 B of wavefront state per slot,
-    // 180 GB of HBM3e on B200 -> ~390 Mi slots): the persistent queue walkers need a DEEP queue -- with 4 Mi-slot
-    // tiles a walk launch got ~0.5 M rays for 151 k lanes and spent a quarter of its time in the drain tail
-    size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)(ctx->prop.totalGlobalMem / 4 / 116);
+    // default tile: as many slots as a quarter of the device memory holds (wavefront state per slot: ray 32 + hit 32 +
+    // throughput 16 bytes, and per light a 32-byte shadow ray and a 4-byte queue entry; 180 GB of HBM3e on B200 -> ~300 Mi
+    // slots with two lights): the persistent queue walkers need a DEEP queue -- with 4 Mi-slot tiles a walk launch got
+    // ~0.5 M rays for 151 k lanes and spent a quarter of its time in the drain tail
+    const size_t nlq = scene->lights.size() ? scene->lights.size() : 1;
+    const size_t slot_bytes = 80 + 36 * nlq;
+    size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)(ctx->prop.totalGlobalMem / 4 / slot_bytes);
     if (want < ((size_t)1 << 22)) want = (size_t)1 << 22;
+    if (want * nlq > 0xFFFFFFFFull) want = 0xFFFFFFFFull / nlq;   // queue entries are light * tile_slots + slot in 32 bits
     size_t px_per_tile = want / r->slots_pp;
     if (px_per_tile == 0) px_per_tile = 1;
     if (px_per_tile > r->pixels) px_per_tile = r->pixels;

@@ -18,6 +18,7 @@ struct rt_ctx {
     unsigned* st_hit = nullptr;
     unsigned* st_cells = nullptr;
     unsigned* st_tests = nullptr;
+    unsigned long long* st_totals = nullptr;   // rt_set_walk_totals: 8 counters accumulated by every grid-walk launch
     unsigned long long launches = 0;   // kernels launched through this context
     // scratch allocations (grid build, rpp == 1 launcher) come from a pool of the context's own that KEEPS its memory
     // between calls: the device's default pool releases everything at each synchronisation, which made a per-pass

@@ -476,11 +476,8 @@ RT_DEV uchar4 cellParityColor(const Hit& h, float shade) {
     return mkPixel((float)((h.cx % 2) + 1) * s, (float)((h.cy % 2) + 1) * s, (float)((h.cz % 2) + 1) * s);
 }
 
-// Optional per-pixel statistics sinks of rt_set_walk_stats (hit-id parity, work counters of the roofline).
-struct A07Stats { unsigned* hit; unsigned* cells; unsigned* tests; };
-
 template <int PRIM, bool OCC, bool STATS>
-__global__ void k_a07_trace(uchar4* pixels, CamArg fcam, Ray* rays, GridView g, const float4* normals, A07Stats sp) {
+__global__ void k_a07_trace(uchar4* pixels, CamArg fcam, Ray* rays, GridView g, const float4* normals, StatPtrs sp) {
     unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     Camera cam = floatToCamera(fcam.v);
     if (id >= cam.cols * cam.rows) return;
@@ -492,11 +489,12 @@ __global__ void k_a07_trace(uchar4* pixels, CamArg fcam, Ray* rays, GridView g, 
     RayR ray = loadRay(rays + id);
     if (ray.mint == ray.maxt) return;
     AabbHit binter = interAABB(ray.o, ray.d, g.bound);
-    if (!binter.v) return;
+    WalkStats ws = {0, 0, 0};
+    if (!binter.v) { if (STATS) tallyWalk(sp.totals, 0, ws, false); return; }
     // spheres: inclusive test; triangles: EXCLUSIVE in A07 (A07/code.cl:195, quirk Q9)
-    WalkStats ws = {0, 0};
     Hit h = gridWalk<PRIM, false, false, STATS, OCC>(ray.o, ray.d, ray.maxt, g, binter, &ws);
     if (STATS) {
+        tallyWalk(sp.totals, 1, ws, h.i != 0xFFFFFFFFu);
         if (sp.hit) sp.hit[id] = h.i;
         if (sp.cells) sp.cells[id] = (unsigned)ws.cells;
         if (sp.tests) sp.tests[id] = (unsigned)ws.tests;
@@ -575,15 +573,31 @@ __global__ void k_a089_initShadowTrace(Ray* shadow_rays, const Poi8* pois, unsig
     storeRay(shadow_rays + id, makeRay(org, light_pos));
 }
 
-template <int PRIM>
-__global__ void k_a089_closest(unsigned total, Poi8* pois, Ray* rays, GridView g, const float4* normals, const unsigned* matid) {
+// STATS = the sinks of rt_set_walk_stats / rt_set_walk_totals are on (instrumented runs only)
+RT_DEV void a089Stats(const StatPtrs& sp, unsigned id, const Hit& h, const WalkStats& ws) {
+    tallyWalk(sp.totals, 1, ws, h.i != 0xFFFFFFFFu);
+    if (sp.hit) sp.hit[id] = h.i;
+    if (sp.cells) sp.cells[id] = (unsigned)ws.cells;
+    if (sp.tests) sp.tests[id] = (unsigned)ws.tests;
+}
+RT_DEV void a089StatsInit(const StatPtrs& sp, unsigned id) {
+    if (sp.hit) sp.hit[id] = 0xFFFFFFFFu;
+    if (sp.cells) sp.cells[id] = 0;
+    if (sp.tests) sp.tests[id] = 0;
+}
+
+template <int PRIM, bool STATS>
+__global__ void k_a089_closest(unsigned total, Poi8* pois, Ray* rays, GridView g, const float4* normals, const unsigned* matid, StatPtrs sp) {
     unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= total) return;
+    if (STATS) a089StatsInit(sp, id);
     RayR ray = loadRay(rays + id);
     if (ray.mint == ray.maxt) return;
     AabbHit binter = interAABB(ray.o, ray.d, g.bound);
-    if (!binter.v) return;
-    Hit h = gridWalk<PRIM, false, true, false>(ray.o, ray.d, ray.maxt, g, binter, nullptr);
+    WalkStats ws = {0, 0, 0};
+    if (!binter.v) { if (STATS) tallyWalk(sp.totals, 0, ws, false); return; }
+    Hit h = gridWalk<PRIM, false, true, STATS>(ray.o, ray.d, ray.maxt, g, binter, &ws);
+    if (STATS) a089Stats(sp, id, h, ws);
     if (h.i == 0xFFFFFFFFu) return;
     rays[id].maxt = h.t;
     f3 p = getPoint(ray.o, ray.d, h.t);
@@ -601,15 +615,18 @@ __global__ void k_a089_closest(unsigned total, Poi8* pois, Ray* rays, GridView g
     pois[id].matId = (int)__ldg(matid + h.i);
 }
 
-template <int PRIM>
-__global__ void k_a089_any(unsigned total, Ray* shadow_rays, GridView g) {
+template <int PRIM, bool STATS>
+__global__ void k_a089_any(unsigned total, Ray* shadow_rays, GridView g, StatPtrs sp) {
     unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= total) return;
+    if (STATS) a089StatsInit(sp, id);
     RayR ray = loadRay(shadow_rays + id);
     if (ray.mint == ray.maxt) return;
     AabbHit binter = interAABB(ray.o, ray.d, g.bound);
-    if (!binter.v) return;
-    Hit h = gridWalk<PRIM, true, true, false>(ray.o, ray.d, ray.maxt, g, binter, nullptr);
+    WalkStats ws = {0, 0, 0};
+    if (!binter.v) { if (STATS) tallyWalk(sp.totals, 0, ws, false); return; }
+    Hit h = gridWalk<PRIM, true, true, STATS>(ray.o, ray.d, ray.maxt, g, binter, &ws);
+    if (STATS) a089Stats(sp, id, h, ws);
     if (h.i != 0xFFFFFFFFu) {
         shadow_rays[id].maxt = h.t;
         shadow_rays[id].mint = h.t;
@@ -767,8 +784,23 @@ __global__ void __launch_bounds__(kBlock) k_a089_frame(const __grid_constant__ A
 #define RT_GRID1(n) rt_blocks((n), kBlock), kBlock, 0, ctx->stream
 
 template <int PRIM>
+void launchA089Closest(rt_ctx* ctx, unsigned total, void* pois, void* rays, const GridView& g, const void* normals, const void* matid) {
+    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests, ctx->st_totals};
+    if (sp.hit || sp.cells || sp.tests || sp.totals)
+        k_a089_closest<PRIM, true><<<RT_GRID1(total)>>>(total, (Poi8*)pois, (Ray*)rays, g, (const float4*)normals, (const unsigned*)matid, sp);
+    else
+        k_a089_closest<PRIM, false><<<RT_GRID1(total)>>>(total, (Poi8*)pois, (Ray*)rays, g, (const float4*)normals, (const unsigned*)matid, sp);
+}
+template <int PRIM>
+void launchA089Any(rt_ctx* ctx, unsigned total, void* shadow_rays, const GridView& g) {
+    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests, ctx->st_totals};
+    if (sp.hit || sp.cells || sp.tests || sp.totals) k_a089_any<PRIM, true><<<RT_GRID1(total)>>>(total, (Ray*)shadow_rays, g, sp);
+    else k_a089_any<PRIM, false><<<RT_GRID1(total)>>>(total, (Ray*)shadow_rays, g, sp);
+}
+
+template <int PRIM>
 void launchA07(rt_ctx* ctx, size_t n, void* pixels, const float* fcam, void* rays, const GridView& g, const void* normals) {
-    A07Stats sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests};
+    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests};
     const bool stats = sp.hit || sp.cells || sp.tests;
     if (stats) {
         if (g.occ) k_a07_trace<PRIM, true, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)normals, sp);
@@ -971,8 +1003,7 @@ int rt_a09_sphereTrace(rt_ctx* ctx, unsigned total_rays, void* pois, void* rays,
     RT_CHECK_CTX(ctx);
     if (!pois || !rays || !spheres || !s_matid || !s_box_size || !bound || !n_slabs) return RT_ERR_INVALID;
     if (!total_rays) return RT_OK;
-    k_a089_closest<PRIM_SPHERE><<<RT_GRID1(total_rays)>>>(total_rays, (Poi8*)pois, (Ray*)rays, mkGrid(spheres, s_box_size, bound, n_slabs), nullptr,
-                                                          (const unsigned*)s_matid);
+    launchA089Closest<PRIM_SPHERE>(ctx, total_rays, pois, rays, mkGrid(spheres, s_box_size, bound, n_slabs), nullptr, s_matid);
     RT_LAUNCH_CHECK(ctx, "sphereTrace");
     return RT_OK;
 }
@@ -986,8 +1017,7 @@ int rt_a09_triangleTrace(rt_ctx* ctx, unsigned total_rays, void* pois, void* ray
     RT_CHECK_CTX(ctx);
     if (!pois || !rays || !t_pos || !t_normal || !t_matid || !t_box_size || !bound || !n_slabs) return RT_ERR_INVALID;
     if (!total_rays) return RT_OK;
-    k_a089_closest<PRIM_TRIANGLE><<<RT_GRID1(total_rays)>>>(total_rays, (Poi8*)pois, (Ray*)rays, mkGrid(t_pos, t_box_size, bound, n_slabs),
-                                                            (const float4*)t_normal, (const unsigned*)t_matid);
+    launchA089Closest<PRIM_TRIANGLE>(ctx, total_rays, pois, rays, mkGrid(t_pos, t_box_size, bound, n_slabs), t_normal, t_matid);
     RT_LAUNCH_CHECK(ctx, "triangleTrace");
     return RT_OK;
 }
@@ -1001,7 +1031,7 @@ int rt_a09_sphereShadowTrace(rt_ctx* ctx, unsigned total_rays, void* shadow_rays
     RT_CHECK_CTX(ctx);
     if (!shadow_rays || !spheres || !s_box_size || !bound || !n_slabs) return RT_ERR_INVALID;
     if (!total_rays) return RT_OK;
-    k_a089_any<PRIM_SPHERE><<<RT_GRID1(total_rays)>>>(total_rays, (Ray*)shadow_rays, mkGrid(spheres, s_box_size, bound, n_slabs));
+    launchA089Any<PRIM_SPHERE>(ctx, total_rays, shadow_rays, mkGrid(spheres, s_box_size, bound, n_slabs));
     RT_LAUNCH_CHECK(ctx, "sphereShadowTrace");
     return RT_OK;
 }
@@ -1015,7 +1045,7 @@ int rt_a09_triangleShadowTrace(rt_ctx* ctx, unsigned total_rays, void* shadow_ra
     RT_CHECK_CTX(ctx);
     if (!shadow_rays || !t_pos || !t_box_size || !bound || !n_slabs) return RT_ERR_INVALID;
     if (!total_rays) return RT_OK;
-    k_a089_any<PRIM_TRIANGLE><<<RT_GRID1(total_rays)>>>(total_rays, (Ray*)shadow_rays, mkGrid(t_pos, t_box_size, bound, n_slabs));
+    launchA089Any<PRIM_TRIANGLE>(ctx, total_rays, shadow_rays, mkGrid(t_pos, t_box_size, bound, n_slabs));
     RT_LAUNCH_CHECK(ctx, "triangleShadowTrace");
     return RT_OK;
 }

@@ -11,7 +11,6 @@ namespace {
 
 constexpr unsigned kBlock = 256;
 
-struct StatPtrs { unsigned* hit; unsigned* cells; unsigned* tests; };
 
 // ---------------------------------------------------------------------------- initAcu
 __global__ void k_initAcu(float4* acu, unsigned total_rays) {   // A10/code.cl:448-456
@@ -161,10 +160,11 @@ __global__ void k_closestTrace(unsigned total_rays, Poi10* pois, Ray* rays, Grid
     RayR ray = loadRay(rays + id);
     if (ray.mint == ray.maxt) return;
     AabbHit binter = interAABB(ray.o, ray.d, g.bound);
-    if (!binter.v) return;
-    WalkStats ws = {0, 0};
+    WalkStats ws = {0, 0, 0};
+    if (!binter.v) { if (STATS) tallyWalk(sp.totals, 0, ws, false); return; }
     Hit h = gridWalk<PRIM, false, true, STATS>(ray.o, ray.d, ray.maxt, g, binter, &ws);
     if (STATS) {
+        tallyWalk(sp.totals, 1, ws, h.i != 0xFFFFFFFFu);
         if (sp.hit) sp.hit[id] = h.i;
         if (sp.cells) sp.cells[id] = (unsigned)ws.cells;
         if (sp.tests) sp.tests[id] = (unsigned)ws.tests;
@@ -204,10 +204,11 @@ __global__ void k_anyTrace(unsigned total_rays, Ray* shadow_rays, GridView g, St
     RayR ray = loadRay(shadow_rays + id);
     if (ray.mint == ray.maxt) return;
     AabbHit binter = interAABB(ray.o, ray.d, g.bound);
-    if (!binter.v) return;
-    WalkStats ws = {0, 0};
+    WalkStats ws = {0, 0, 0};
+    if (!binter.v) { if (STATS) tallyWalk(sp.totals, 0, ws, false); return; }
     Hit h = gridWalk<PRIM, true, true, STATS>(ray.o, ray.d, ray.maxt, g, binter, &ws);
     if (STATS) {
+        tallyWalk(sp.totals, 1, ws, h.i != 0xFFFFFFFFu);
         if (sp.hit) sp.hit[id] = h.i;
         if (sp.cells) sp.cells[id] = (unsigned)ws.cells;
         if (sp.tests) sp.tests[id] = (unsigned)ws.tests;
@@ -280,8 +281,8 @@ template <int PRIM>
 int launchClosest(rt_ctx* ctx, unsigned total_rays, void* pois, void* rays, GridView g, const void* normals, const void* matid,
                   unsigned scalar_matid, const char* name) {
     if (!total_rays) return RT_OK;
-    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests};
-    bool stats = sp.hit || sp.cells || sp.tests;
+    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests, ctx->st_totals};
+    bool stats = sp.hit || sp.cells || sp.tests || sp.totals;
     dim3 grid(rt_blocks(total_rays, kBlock));
     if (stats)
         k_closestTrace<PRIM, true><<<grid, kBlock, 0, ctx->stream>>>(total_rays, (Poi10*)pois, (Ray*)rays, g, (const float4*)normals,
@@ -296,8 +297,8 @@ int launchClosest(rt_ctx* ctx, unsigned total_rays, void* pois, void* rays, Grid
 template <int PRIM>
 int launchAny(rt_ctx* ctx, unsigned total_rays, void* shadow, GridView g, const char* name) {
     if (!total_rays) return RT_OK;
-    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests};
-    bool stats = sp.hit || sp.cells || sp.tests;
+    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests, ctx->st_totals};
+    bool stats = sp.hit || sp.cells || sp.tests || sp.totals;
     dim3 grid(rt_blocks(total_rays, kBlock));
     if (stats)
         k_anyTrace<PRIM, true><<<grid, kBlock, 0, ctx->stream>>>(total_rays, (Ray*)shadow, g, sp);

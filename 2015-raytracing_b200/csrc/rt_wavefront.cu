@@ -65,7 +65,7 @@ RT_DEV void closestSet(const SetDev& s, RayR& ray, PoiR& poi, unsigned* prof) {
     AabbHit binter = interAABB(ray.o, ray.d, s.g.bound);
     if (!binter.v) return;
     Hit h;
-    WalkStats ws = {0, 0};
+    WalkStats ws = {0, 0, 0};
     if (s.g.n == 1 && (s.kind == PRIM_SPHERE || s.pre_ng)) {
         if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, false, STATS>(ray.o, ray.d, ray.maxt, s.g, nullptr, nullptr, binter, &ws);
         else h = singleCellWalk<PRIM_TRIANGLE, false, STATS>(ray.o, ray.d, ray.maxt, s.g, s.pre_ng, s.pre_pe, binter, &ws);
@@ -75,6 +75,7 @@ RT_DEV void closestSet(const SetDev& s, RayR& ray, PoiR& poi, unsigned* prof) {
         prof[1]++;
         prof[2] += (unsigned)ws.cells;
         prof[s.kind == PRIM_SPHERE ? 3 : 4] += (unsigned)ws.tests;
+        prof[15] += (unsigned)ws.front;
         if (h.i != 0xFFFFFFFFu) prof[s.kind == PRIM_SPHERE ? 5 : (s.matid ? 6 : 7)]++;
     }
     if (h.i == 0xFFFFFFFFu) return;
@@ -99,7 +100,7 @@ RT_DEV void anySet(const SetDev& s, RayR& sr, unsigned* prof) {
     AabbHit binter = interAABB(sr.o, sr.d, s.g.bound);
     if (!binter.v) return;
     Hit h;
-    WalkStats ws = {0, 0};
+    WalkStats ws = {0, 0, 0};
     if (s.g.n == 1 && (s.kind == PRIM_SPHERE || s.pre_ng)) {
         if (s.kind == PRIM_SPHERE) h = singleCellWalk<PRIM_SPHERE, true, STATS>(sr.o, sr.d, sr.maxt, s.g, nullptr, nullptr, binter, &ws);
         else h = singleCellWalk<PRIM_TRIANGLE, true, STATS>(sr.o, sr.d, sr.maxt, s.g, s.pre_ng, s.pre_pe, binter, &ws);
@@ -109,17 +110,21 @@ RT_DEV void anySet(const SetDev& s, RayR& sr, unsigned* prof) {
         prof[9]++;
         prof[10] += (unsigned)ws.cells;
         prof[s.kind == PRIM_SPHERE ? 11 : 12] += (unsigned)ws.tests;
+        prof[15] += (unsigned)ws.front;
         if (h.i != 0xFFFFFFFFu) prof[13]++;
     }
     if (h.i != 0xFFFFFFFFu) { sr.maxt = h.t; sr.mint = h.t; }
     else sr.maxt = h.t;
 }
 
-// Profile build only: add this thread's counters [lo,hi) to row `set` of the global table (one atomic
-// per counter per converged group of lanes) and clear them.
+// Profile build only: add this thread's counters [lo,hi) to row `set` of the global table and clear them.  The lanes that
+// happen to execute this together may stand in DIFFERENT iterations of the caller's loop over sets (after divergence the
+// hardware regroups lanes by program counter, not by iteration), so they are grouped by `set` first: one atomic per counter
+// per group.  (Round 1 reduced over __activemask() alone and credited some counts to a neighbouring set's row -- column
+// sums were right, rows were off by ~0.3 %; tests/test_gpu_gates.py checks the rows against the instrumented oracle now.)
 RT_DEV void flushProfile(unsigned* prof, unsigned long long* table, int set, int lo, int hi) {
-    unsigned m = __activemask();
-    int leader = __ffs(m) - 1;
+    const unsigned m = __match_any_sync(__activemask(), set);
+    const int leader = __ffs(m) - 1;
     for (int q = lo; q < hi; q++) {
         unsigned v = __reduce_add_sync(m, prof[q]);
         if ((int)(threadIdx.x & 31) == leader && v) atomicAdd(table + set * 16 + q, (unsigned long long)v);
@@ -165,7 +170,7 @@ RT_DEV void closestAllSets(const SceneDev& sc, RayR& ray, PoiR& poi, unsigned* p
     for (int s = 0; s < sc.n_sets; s++) {
         if (sc.sets[s].use_occ) closestSet<true, STATS>(sc.sets[s], ray, poi, prof);
         else closestSet<false, STATS>(sc.sets[s], ray, poi, prof);
-        if (STATS) flushProfile(prof, table, s, 0, 8);
+        if (STATS) { flushProfile(prof, table, s, 0, 8); flushProfile(prof, table, s, 15, 16); }
     }
 }
 
@@ -179,7 +184,7 @@ RT_DEV void shadeLight(const SceneDev& sc, const LightDev& L, PoiR& poi, int& se
     for (int s = 0; s < sc.n_sets; s++) {
         if (sc.sets[s].use_occ) anySet<true, STATS>(sc.sets[s], sr, prof);
         else anySet<false, STATS>(sc.sets[s], sr, prof);
-        if (STATS) flushProfile(prof, table, s, 8, 14);
+        if (STATS) { flushProfile(prof, table, s, 8, 14); flushProfile(prof, table, s, 15, 16); }
     }
     f3 shade = neeShade(poi.p, poi.n, sr.d, sr.maxt != sr.mint, L.scene);
     float4 color = __ldg(sc.materials + poi.matId);
@@ -364,21 +369,51 @@ struct WaveState {
     float4* ray;      // [2n]
     float4* poi;      // [2n]
     float4* atte;     // [n]
-    float4* sh;       // [2n]
-    unsigned* queue;  // [n]
+    float4* sh;       // [lights][2n]: light l's shadow ray of slot id = sh[2l*n + id] (o, mint), sh[(2l+1)*n + id] (d, maxt)
+    unsigned* queue;  // [n * lights]: closest-hit walks queue slot ids, any-hit walks queue light * n + slot
     unsigned* qctr;   // {count, head} per walk stage
 };
 
 // What one per-slot stage kernel does, in this order (all fields uniform across the grid):
-//   shade_light >= 0 : sceneRender for that light with the current shadow ray
+//   shade            : sceneRender for EVERY light, in light order, with that light's current shadow ray
 //   gen == 1/2       : initTrace / bouncePaths -> new ray
 //   light_render     : lightRender for every light (primary segment, after the closest pass)
-//   shadow_light >= 0: initShadowTrace for that light -> new shadow ray
-//   inline sets [set_lo, set_hi) against the current ray (kind 0 = closest, 1 = any hit)
-//   push_set >= 0    : AABB-test the ray against that heavy set and enqueue the slot
+//   shadow           : initShadowTrace for EVERY light, in light order -> one new shadow ray per light
+//   inline sets [set_lo, set_hi) against the current ray (kind 0 = closest) or against every light's shadow ray (kind 1)
+//   push_set >= 0    : AABB-test the ray(s) against that heavy set and enqueue the slot (kind 1: one entry per light)
+//
+// All lights of a segment travel TOGETHER (one shadow ray buffer per light): the random draws of a slot do not depend on the
+// shadow results -- initShadowTrace draws iff matId >= 0 (A10/code.cl:641-651) and neither the shadow traces nor sceneRender
+// touch matId -- so drawing light 1's sample right after light 0's is the reference's draw order (quirk Q8), and the
+// sceneRender calls still run in light order afterwards (atte *= colour per light, quirk Q3).  Per tile that is 1 + 6 * 2
+// stage launches and 6 any-hit walks per heavy set instead of 1 + 6 * (1 + L) and 6 * L, with L-times deeper any-hit queues.
 struct StageOp {
-    int shade_light, gen, light_render, shadow_light, kind, set_lo, set_hi, push_set, qslot;
+    int shade, gen, light_render, shadow, kind, set_lo, set_hi, push_set, qslot;
+    int shade_lo, shade_hi;   // lights whose sceneRender runs when `shade`
+    int light_lo, light_hi;   // lights whose shadow rays this stage generates / traces (kind 1)
 };
+
+// Loads / stores of the per-slot wavefront state (rays, hit records, shadow rays, queues, seeds, accumulators): every
+// byte is touched once per kernel and the tile is gigabytes, so nothing of it survives in the L2 until the next kernel
+// anyway.  RT_STREAM_CS = 1 marks these accesses evict-first (ld/st.global.cs) so that they stop displacing the scene data
+// (cell table, occupancy bits, face vectors) the walkers re-read all the time.
+#ifndef RT_STREAM_CS
+#define RT_STREAM_CS 0
+#endif
+template <class T> RT_DEV T ldS(const T* p) {
+#if RT_STREAM_CS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <class T> RT_DEV void stS(T* p, T v) {
+#if RT_STREAM_CS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 RT_DEV void pushTask(bool want, unsigned id, unsigned* queue, unsigned* count) {
     unsigned m = __ballot_sync(0xffffffffu, want);
@@ -388,62 +423,60 @@ RT_DEV void pushTask(bool want, unsigned id, unsigned* queue, unsigned* count) {
     int leader = __ffs(m) - 1;
     if ((int)lane == leader) base = atomicAdd(count, (unsigned)__popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (want) queue[base + __popc(m & ((1u << lane) - 1u))] = id;
+    if (want) stS(queue + base + __popc(m & ((1u << lane) - 1u)), id);
 }
 
 #ifndef RT_STAGE_MINB
 #define RT_STAGE_MINB 5
 #endif
-// GEN / LR / SHADE / SHADOW / KIND mirror StageOp's gen, light_render, shade_light >= 0, shadow_light >= 0 and kind; they are
-// template parameters so that each of the few stage shapes a pass is made of gets its own register allocation (the
-// all-in-one kernel needed 80 registers or spilled ~400 B at 64).  The light indices and set ranges stay run-time values.
+// GEN / LR / SHADE / SHADOW / KIND mirror StageOp's gen, light_render, shade, shadow and kind; they are template
+// parameters so that each of the few stage shapes a pass is made of gets its own register allocation (the
+// all-in-one kernel needed 80 registers or spilled ~400 B at 64).  The set ranges stay run-time values.
 template <int GEN, bool LR, bool SHADE, bool SHADOW, int KIND>
 __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_constant__ SceneDev sc, const __grid_constant__ PathArgs a,
                                                const __grid_constant__ WaveState w, const __grid_constant__ StageOp op) {
-    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
-    bool inb = id < a.n_local;
+    const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inb = id < a.n_local;
+    const unsigned n = a.n_local;
+    const int nl = sc.n_lights;
     unsigned n_closest = 0, n_any = 0;
     bool want_push = false;
+    PoiR poi;
+    poi.p = mk3(0.f, 0.f, 0.f); poi.n = mk3(0.f, 0.f, 0.f); poi.atte = mk3(1.f, 1.f, 1.f); poi.matId = -1;
+    int seed = 0;
+    bool seed_loaded = false, seed_dirty = false;
     if (inb) {
-        const unsigned n = a.n_local;
-        PoiR poi;
-        RayR ray, sr;
-        bool poi_dirty = false, ray_dirty = false, sr_dirty = false, atte_dirty = false;
+        RayR ray;
+        bool poi_dirty = false, ray_dirty = false, atte_dirty = false;
         // ---- load what this stage needs
-        if (GEN != 1) {
-            float4 p0 = w.poi[id], p1 = w.poi[n + id];
+        if (GEN != 1 && (SHADE || GEN == 2 || LR || SHADOW || KIND == 0)) {
+            float4 p0 = ldS(w.poi + id), p1 = ldS(w.poi + n + id);
             poi.p = mk3(p0.x, p0.y, p0.z); poi.matId = __float_as_int(p0.w);
             poi.n = mk3(p1.x, p1.y, p1.z);
-            float4 at = w.atte[id];
-            poi.atte = mk3(at.x, at.y, at.z);
         }
         bool need_ray = (GEN == 0) && (LR || (KIND == 0 && (op.set_hi > op.set_lo || op.push_set >= 0)));
         if (need_ray) {
-            float4 r0 = w.ray[id], r1 = w.ray[n + id];
+            float4 r0 = ldS(w.ray + id), r1 = ldS(w.ray + n + id);
             ray.o = mk3(r0.x, r0.y, r0.z); ray.mint = r0.w;
             ray.d = mk3(r1.x, r1.y, r1.z); ray.maxt = r1.w;
         }
-        bool need_sr = SHADE || (!SHADOW && KIND == 1 && (op.set_hi > op.set_lo || op.push_set >= 0));
-        if (need_sr) {
-            float4 s0 = w.sh[id], s1 = w.sh[n + id];
-            sr.o = mk3(s0.x, s0.y, s0.z); sr.mint = s0.w;
-            sr.d = mk3(s1.x, s1.y, s1.z); sr.maxt = s1.w;
-        }
-        int seed = 0;
-        bool seed_loaded = false, seed_dirty = false;
         float4 acu;
         bool acu_loaded = false;
-        // ---- sceneRender of the previous shadow ray (A10/code.cl:1323-1364)
+        // ---- sceneRender of the previous shadow rays, light by light (A10/code.cl:1323-1364)
         if (SHADE && poi.matId >= 0) {
-            const LightDev& L = sc.lights[op.shade_light];
-            f3 shade = neeShade(poi.p, poi.n, sr.d, sr.maxt != sr.mint, L.scene);
+            float4 at = ldS(w.atte + id);
+            poi.atte = mk3(at.x, at.y, at.z);
+            acu = ldS(a.acu + id); acu_loaded = true;
             float4 color = __ldg(sc.materials + poi.matId);
             f3 c = mk3(color.x, color.y, color.z);
-            f3 contrib = (c * poi.atte) * shade;
-            poi.atte = poi.atte * c;
-            atte_dirty = true;
-            acu = a.acu[id]; acu_loaded = true;
-            acu = make_float4(acu.x + contrib.x, acu.y + contrib.y, acu.z + contrib.z, acu.w + 1.0f);
+            for (int l = op.shade_lo; l < op.shade_hi; l++) {
+                float4 s0 = ldS(w.sh + (size_t)(2 * l) * n + id), s1 = ldS(w.sh + (size_t)(2 * l + 1) * n + id);
+                f3 shade = neeShade(poi.p, poi.n, mk3(s1.x, s1.y, s1.z), s1.w != s0.w, sc.lights[l].scene);
+                f3 contrib = (c * poi.atte) * shade;
+                poi.atte = poi.atte * c;   // per light (quirk Q3)
+                acu = make_float4(acu.x + contrib.x, acu.y + contrib.y, acu.z + contrib.z, acu.w + 1.0f);
+            }
+            atte_dirty = op.shade_hi > op.shade_lo;
         }
         // ---- new ray
         if (GEN == 1) {   // initTrace (A10/code.cl:458-543)
@@ -454,9 +487,6 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
             unsigned col = (unsigned)(pix % cam.cols), row = (unsigned)(pix / cam.cols);
             ray.o = mk3(0.f, 0.f, 0.f); ray.d = mk3(0.f, 0.f, 0.f);
             ray.mint = RT_INF; ray.maxt = RT_INF;
-            poi.p = mk3(0.f, 0.f, 0.f); poi.n = mk3(0.f, 0.f, 0.f);
-            poi.atte = mk3(1.0f, 1.0f, 1.0f);
-            poi.matId = -1;
             poi_dirty = atte_dirty = true;
             bool have_ray = true;
             f2 coord;
@@ -483,7 +513,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
             if (ray.mint != ray.maxt) n_closest++;
         } else if (GEN == 2) {   // bouncePaths (A10/code.cl:581-598)
             if (poi.matId >= 0) {
-                seed = a.seeds[id]; seed_loaded = true;
+                seed = ldS(a.seeds + id); seed_loaded = true;
                 getHemisphereRay(poi.p, poi.n, seed, ray.o, ray.d);
                 seed_dirty = true;
                 ray.mint = 0.0f; ray.maxt = RT_INF;
@@ -496,7 +526,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
         }
         // ---- lightRender for every light (A10/code.cl:600-629)
         if (LR) {
-            for (int l = 0; l < sc.n_lights; l++) {
+            for (int l = 0; l < nl; l++) {
                 if (ray.mint == ray.maxt) continue;
                 const LightArg& L = sc.lights[l].light;
                 f3 irradiance = normalize(mk3(L.v[6], L.v[7], L.v[8]));
@@ -506,24 +536,11 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
                 ray_dirty = true;
                 poi.matId = -1;
                 poi_dirty = true;
-                if (!acu_loaded) { acu = a.acu[id]; acu_loaded = true; }
+                if (!acu_loaded) { acu = ldS(a.acu + id); acu_loaded = true; }
                 acu = make_float4(acu.x + irradiance.x, acu.y + irradiance.y, acu.z + irradiance.z, acu.w + 1.0f);
             }
         }
-        // ---- new shadow ray (A10/code.cl:631-673)
-        if (SHADOW) {
-            if (poi.matId >= 0) {
-                if (!seed_loaded) { seed = a.seeds[id]; seed_loaded = true; }
-                sr = makeShadowRay(poi.p, poi.n, sc.lights[op.shadow_light].shadow, seed);
-                seed_dirty = true;
-                if (sr.mint != sr.maxt) n_any++;
-            } else {
-                sr.o = mk3(0.f, 0.f, 0.f); sr.d = mk3(0.f, 0.f, 0.f);
-                sr.mint = RT_INF; sr.maxt = RT_INF;
-            }
-            sr_dirty = true;
-        }
-        // ---- small sets inline, in set order
+        // ---- small sets inline against the ray, in set order
         if (KIND == 0) {
             for (int s = op.set_lo; s < op.set_hi; s++) {
                 float m0 = ray.maxt; int id0 = poi.matId;
@@ -531,32 +548,63 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
                 if (ray.maxt != m0 || poi.matId != id0) { ray_dirty = true; poi_dirty = true; }
             }
             if (op.push_set >= 0 && ray.mint != ray.maxt) want_push = interAABB(ray.o, ray.d, sc.sets[op.push_set].g.bound).v;
-        } else {
-            for (int s = op.set_lo; s < op.set_hi; s++) {
-                float m0 = sr.mint, x0 = sr.maxt;
-                anySet1(sc.sets[s], sr);
-                if (sr.mint != m0 || sr.maxt != x0) sr_dirty = true;
-            }
-            if (op.push_set >= 0 && sr.mint != sr.maxt) want_push = interAABB(sr.o, sr.d, sc.sets[op.push_set].g.bound).v;
         }
         // ---- write back
         if (ray_dirty) {
-            w.ray[id] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
-            w.ray[n + id] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+            stS(w.ray + (id), make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint));
+            stS(w.ray + (n + id), make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt));
         }
         if (poi_dirty) {
-            w.poi[id] = make_float4(poi.p.x, poi.p.y, poi.p.z, __int_as_float(poi.matId));
-            w.poi[n + id] = make_float4(poi.n.x, poi.n.y, poi.n.z, 0.f);
+            stS(w.poi + (id), make_float4(poi.p.x, poi.p.y, poi.p.z, __int_as_float(poi.matId)));
+            stS(w.poi + (n + id), make_float4(poi.n.x, poi.n.y, poi.n.z, 0.f));
         }
-        if (atte_dirty) w.atte[id] = make_float4(poi.atte.x, poi.atte.y, poi.atte.z, 0.f);
-        if (sr_dirty) {
-            w.sh[id] = make_float4(sr.o.x, sr.o.y, sr.o.z, sr.mint);
-            w.sh[n + id] = make_float4(sr.d.x, sr.d.y, sr.d.z, sr.maxt);
-        }
-        if (seed_dirty) a.seeds[id] = seed;
-        if (acu_loaded) a.acu[id] = acu;
+        if (atte_dirty) stS(w.atte + id, make_float4(poi.atte.x, poi.atte.y, poi.atte.z, 0.f));
+        if (acu_loaded) stS(a.acu + id, acu);
     }
-    if (op.push_set >= 0) pushTask(want_push, id, w.queue, w.qctr + 2 * op.qslot);
+    if (KIND == 0) {
+        if (op.push_set >= 0) pushTask(want_push, id, w.queue, w.qctr + 2 * op.qslot);
+    } else {
+        // ---- every light's shadow ray: new ray (A10/code.cl:631-673), small sets inline, push to the heavy set.  The loop
+        // is uniform (pushTask is a warp collective); draws happen in light order from the slot's one seed.
+        const bool trace = op.set_hi > op.set_lo || op.push_set >= 0;
+        for (int l = op.light_lo; l < op.light_hi; l++) {
+            bool want = false;
+            if (inb && (SHADOW || trace)) {
+                RayR sr;
+                bool sr_dirty = false;
+                float4* s0p = w.sh + (size_t)(2 * l) * n + id;
+                float4* s1p = w.sh + (size_t)(2 * l + 1) * n + id;
+                if (SHADOW) {
+                    if (poi.matId >= 0) {
+                        if (!seed_loaded) { seed = ldS(a.seeds + id); seed_loaded = true; }
+                        sr = makeShadowRay(poi.p, poi.n, sc.lights[l].shadow, seed);
+                        seed_dirty = true;
+                        if (sr.mint != sr.maxt) n_any++;
+                    } else {
+                        sr.o = mk3(0.f, 0.f, 0.f); sr.d = mk3(0.f, 0.f, 0.f);
+                        sr.mint = RT_INF; sr.maxt = RT_INF;
+                    }
+                    sr_dirty = true;
+                } else {
+                    float4 s0 = ldS(s0p), s1 = ldS(s1p);
+                    sr.o = mk3(s0.x, s0.y, s0.z); sr.mint = s0.w;
+                    sr.d = mk3(s1.x, s1.y, s1.z); sr.maxt = s1.w;
+                }
+                for (int s = op.set_lo; s < op.set_hi; s++) {
+                    float m0 = sr.mint, x0 = sr.maxt;
+                    anySet1(sc.sets[s], sr);
+                    if (sr.mint != m0 || sr.maxt != x0) sr_dirty = true;
+                }
+                if (op.push_set >= 0 && sr.mint != sr.maxt) want = interAABB(sr.o, sr.d, sc.sets[op.push_set].g.bound).v;
+                if (sr_dirty) {
+                    stS(s0p, make_float4(sr.o.x, sr.o.y, sr.o.z, sr.mint));
+                    stS(s1p, make_float4(sr.d.x, sr.d.y, sr.d.z, sr.maxt));
+                }
+            }
+            if (op.push_set >= 0) pushTask(want, (unsigned)l * n + id, w.queue, w.qctr + 2 * op.qslot);
+        }
+    }
+    if (inb && seed_dirty) stS(a.seeds + id, seed);
     // ray counters: only a stage that generates rays of a kind can have counted any (one redux + one atomic per warp)
     if (GEN != 0) {
         const unsigned t = __reduce_add_sync(0xffffffffu, n_closest);
@@ -586,6 +634,12 @@ constexpr int kRefill = RT_REFILL;
 // fewer but costlier steps, no gain -- so it stays off; kept because the exactness argument is tested.
 #ifndef RT_SKIP2
 #define RT_SKIP2 0
+#endif
+#ifndef RT_OPAQUE_TID
+#define RT_OPAQUE_TID 0
+#endif
+#ifndef RT_PIPE_NG
+#define RT_PIPE_NG 0
 #endif
 constexpr int kStepBurst = RT_STEP_BURST;   // empty-cell steps per outer iteration
 constexpr int kWalkWarps = 8;               // warps per block
@@ -641,13 +695,24 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
     for (unsigned i = threadIdx.x; i < 8192; i += blockDim.x) s_macro[i] = set.macro_occ[i];
     __syncthreads();
     const unsigned mshift = set.macro_shift, mn = set.macro_n;
-    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#if RT_OPAQUE_TID
+    // ptxas otherwise REMATERIALISES lane / warp id from SR_TID.X (a slow S2R) all over the hot loop instead of keeping
+    // two registers: ncu charged 5.7 % of the kernel's warp instructions to the line that first reads threadIdx
+    asm volatile("" : "+r"(lane));
+    asm volatile("" : "+r"(wid));
+#endif
     const unsigned lt = (1u << lane) - 1u;
     const unsigned FULL = 0xffffffffu;
     const unsigned long long NONE = ~0ull;
     const unsigned count = w.qctr[2 * qslot];
     unsigned* head = w.qctr + 2 * qslot + 1;
-    const float4* src = ANY ? w.sh : w.ray;
+    // any-hit entries are light * n + slot (one shadow ray buffer per light); closest-hit entries are plain slot ids
+    auto rayBase = [&](unsigned e) -> size_t {
+        if (!ANY) return e;
+        const unsigned l = e / n;
+        return (size_t)(2 * l) * n + (e - l * n);
+    };
     const GridView& g = set.g;
     FlatWalker f;
     f.i = f.end = 0;
@@ -696,10 +761,11 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
     auto writeBack = [&]() {
         const Hit& h = f.w.h;
         if (ANY) {
-            float4 s0 = w.sh[slot];
-            w.sh[slot] = make_float4(s0.x, s0.y, s0.z, h.t);
-            float4 s1 = w.sh[n + slot];
-            w.sh[n + slot] = make_float4(s1.x, s1.y, s1.z, h.t);
+            float4* sp = w.sh + rayBase(slot);
+            float4 s0 = ldS(sp);
+            stS(sp, make_float4(s0.x, s0.y, s0.z, h.t));
+            float4 s1 = ldS(sp + n);
+            stS(sp + n, make_float4(s1.x, s1.y, s1.z, h.t));
         } else {
             f3 p = getPoint(f.w.o, f.w.d, h.t);
             f3 nrm;
@@ -713,10 +779,10 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
                 nrm = normalize(interp(h.beta, h.gamma, mk3(n0.x, n0.y, n0.z), mk3(n1.x, n1.y, n1.z), mk3(n2.x, n2.y, n2.z)));
                 m = set.matid ? (int)__ldg(set.matid + h.i) : (int)set.scalar_matid;
             }
-            float4 r1 = w.ray[n + slot];
-            w.ray[n + slot] = make_float4(r1.x, r1.y, r1.z, h.t);
-            w.poi[slot] = make_float4(p.x, p.y, p.z, __int_as_float(m));
-            w.poi[n + slot] = make_float4(nrm.x, nrm.y, nrm.z, 0.f);
+            float4 r1 = ldS(w.ray + n + slot);
+            stS(w.ray + (n + slot), make_float4(r1.x, r1.y, r1.z, h.t));
+            stS(w.poi + (slot), make_float4(p.x, p.y, p.z, __int_as_float(m)));
+            stS(w.poi + (n + slot), make_float4(nrm.x, nrm.y, nrm.z, 0.f));
         }
     };
 
@@ -744,8 +810,9 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
             if (!have) {
                 unsigned idx = base + __popc(idle & lt);
                 if (idx < count) {
-                    slot = w.queue[idx];
-                    float4 r0 = src[slot], r1 = src[n + slot];
+                    slot = ldS(w.queue + idx);
+                    const float4* src = (ANY ? w.sh : w.ray) + rayBase(slot);
+                    float4 r0 = ldS(src), r1 = ldS(src + n);
                     f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
                     AabbHit binter = interAABB(o, d, g.bound);
                     walkInit(f.w, PRIM, o, d, r1.w, g, binter);
@@ -806,24 +873,56 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
         s_best[wid][lane] = NONE;
         __syncwarp();
         unsigned ncand = 0;
-        for (unsigned base = 0; base < P; base += 32) {
+        // owner of pair p = the last pending lane whose list offset is <= p.  Rank it instead of searching:
+        // pending lanes that start before this batch are counted with one ballot, the ones that start inside
+        // it set a bit at their start position (offsets of pending lanes are distinct), and a popc of the
+        // bits up to this lane's position gives the rank into the ordered list of pending lanes.
+        auto pairOf = [&](unsigned base, unsigned& own, unsigned& ref) -> bool {
             const unsigned p = base + lane;
-            const bool valid = p < P;
-            // owner of pair p = the last pending lane whose list offset is <= p.  Rank it instead of searching:
-            // pending lanes that start before this batch are counted with one ballot, the ones that start inside
-            // it set a bit at their start position (offsets of pending lanes are distinct), and a popc of the
-            // bits up to this lane's position gives the rank into the ordered list of pending lanes.
             const unsigned before = __popc(__ballot_sync(FULL, pending && off <= base));
             const unsigned starts = __reduce_or_sync(FULL, (pending && off > base && off < base + 32) ? (1u << (off - base)) : 0u);
             const unsigned rank = before + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));   // >= 1 for valid pairs
-            const unsigned own = s_plist[wid][(rank ? rank : 1u) - 1u];
-            const unsigned ref = __shfl_sync(FULL, f.i, own) + (p - s_poff[wid][(rank ? rank : 1u) - 1u]);
+            own = s_plist[wid][(rank ? rank : 1u) - 1u];
+            ref = __shfl_sync(FULL, f.i, own) + (p - s_poff[wid][(rank ? rank : 1u) - 1u]);
+            return p < P;
+        };
+#if RT_PIPE_NG
+        // software pipeline: the face vector of batch b + 1 is requested BEFORE batch b is culled and tested, so that
+        // its L2 / DRAM latency overlaps that work (ncu: the first use of this load is the kernel's top stall site)
+        unsigned own = 0, ref = 0;
+        bool valid = pairOf(0, own, ref);
+#if RT_PIPE_NG == 1
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (PRIM == PRIM_TRIANGLE && valid) q = ldKeep(set.pre_ng + ref);
+#endif
+#endif
+        for (unsigned base = 0; base < P; base += 32) {
+#if RT_PIPE_NG
+            unsigned own2 = 0, ref2 = 0;
+            bool valid2 = false;
+#if RT_PIPE_NG == 1
+            float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
+            if (base + 32 < P) {
+                valid2 = pairOf(base + 32, own2, ref2);
+#if RT_PIPE_NG == 1
+                if (PRIM == PRIM_TRIANGLE && valid2) q2 = ldKeep(set.pre_ng + ref2);   // register double buffer
+#else
+                if (PRIM == PRIM_TRIANGLE && valid2) prefetchLine<1>(set.pre_ng + ref2);   // 2: no registers held, the line waits in the L1
+#endif
+            }
+#else
+            unsigned own, ref;
+            const bool valid = pairOf(base, own, ref);
+#endif
             bool pass = valid;
             float dv = 0.f;
             if (PRIM == PRIM_TRIANGLE) {
                 const f3 d = mk3(__shfl_sync(FULL, f.w.d.x, own), __shfl_sync(FULL, f.w.d.y, own), __shfl_sync(FULL, f.w.d.z, own));
                 if (valid) {
-                    float4 q = __ldg(set.pre_ng + ref);
+#if RT_PIPE_NG != 1
+                    float4 q = ldKeep(set.pre_ng + ref);
+#endif
                     dv = dot(mk3(q.x, q.y, q.z), d);
                     pass = dv > 0;   // the reference's first rejection (div <= 0), on the precomputed face vector
                 }
@@ -853,6 +952,12 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
                 ncand -= 32;
                 __syncwarp();
             }
+#if RT_PIPE_NG
+            own = own2; ref = ref2; valid = valid2;
+#if RT_PIPE_NG == 1
+            q = q2;
+#endif
+#endif
         }
         if (ncand) testCandidates(ncand);
         __syncwarp();
@@ -894,7 +999,7 @@ void appendTrace(std::vector<Stage>& st, const rt_scene* sc, StageOp first, int 
     bool cur_used = true;   // `first` must be emitted even if empty of set work
     int nset = (int)sc->sets.size();
     int s = 0;
-    StageOp blank = {-1, 0, 0, -1, kind, 0, 0, -1, 0};
+    StageOp blank = {0, 0, 0, 0, kind, 0, 0, -1, 0, 0, 0, first.light_lo, first.light_hi};
     while (s < nset) {
         if (!isHeavy(sc->sets[s])) {
             int e = s;
@@ -916,31 +1021,39 @@ void appendTrace(std::vector<Stage>& st, const rt_scene* sc, StageOp first, int 
     if (cur_used) st.push_back({false, cur, -1, false, 0});
 }
 
+// RT2015_SPLIT_LIGHTS=1 (environment, read once) restores round 1's schedule -- one shadow stage + one any-hit walk per light --
+// for A/B runs; the default sends all lights of a segment through one stage and one walk.
+bool splitLights() {
+    static const bool v = getenv("RT2015_SPLIT_LIGHTS") && atoi(getenv("RT2015_SPLIT_LIGHTS")) != 0;
+    return v;
+}
+
 int buildStages(const rt_render* r, std::vector<Stage>& st) {
     const rt_scene* sc = r->scene;
-    int nl = (int)sc->lights.size();
+    const int nl = (int)sc->lights.size();
+    const int group = splitLights() ? 1 : (nl > 0 ? nl : 1);   // lights per shadow stage
     int qslot = 0;
-    StageOp blank = {-1, 0, 0, -1, 0, 0, 0, -1, 0};
-    int pending_shade = -1;   // light whose sceneRender still has to run
+    const StageOp blank = {0, 0, 0, 0, 0, 0, 0, -1, 0, 0, 0, 0, 0};
+    int shade_lo = 0, shade_hi = 0;   // lights whose sceneRender still has to run
     for (unsigned seg = 0; seg <= r->o.depth; seg++) {
         StageOp g = blank;
-        g.shade_light = pending_shade; pending_shade = -1;
+        g.shade = shade_hi > shade_lo; g.shade_lo = shade_lo; g.shade_hi = shade_hi;
+        shade_lo = shade_hi = 0;
         g.gen = seg == 0 ? 1 : 2;
         appendTrace(st, sc, g, 0, qslot);
-        for (int l = 0; l < nl; l++) {
+        for (int l0 = 0; l0 < nl; l0 += group) {   // lightRender (primary segment), then this group's shadow rays at once
             StageOp h = blank;
-            h.shade_light = pending_shade; pending_shade = -1;
-            if (seg == 0 && l == 0) h.light_render = 1;
-            h.shadow_light = l;
+            h.shade = shade_hi > shade_lo; h.shade_lo = shade_lo; h.shade_hi = shade_hi;
+            h.light_render = seg == 0 && l0 == 0;
+            h.shadow = 1;
+            h.light_lo = l0; h.light_hi = l0 + group < nl ? l0 + group : nl;
             appendTrace(st, sc, h, 1, qslot);
-            pending_shade = l;
-        }
-        if (nl == 0 && seg == 0) {   // lightRender is a no-op without lights; nothing to do
+            shade_lo = h.light_lo; shade_hi = h.light_hi;
         }
     }
-    if (pending_shade >= 0) {
+    if (shade_hi > shade_lo) {
         StageOp f = blank;
-        f.shade_light = pending_shade;
+        f.shade = 1; f.shade_lo = shade_lo; f.shade_hi = shade_hi;
         st.push_back({false, f, -1, false, 0});
     }
     // merge adjacent per-slot stages where the second one carries no set work of its own that
@@ -952,9 +1065,9 @@ int buildStages(const rt_render* r, std::vector<Stage>& st) {
             const StageOp& b = s.op;
             bool a_traces = a.set_hi > a.set_lo || a.push_set >= 0;
             // b's shade/gen/shadow come after a's set work in program order: only merge when a has none
-            if (!a_traces && a.shadow_light < 0 && a.gen == 0 && !a.light_render && b.shade_light < 0) {
+            if (!a_traces && !a.shadow && a.gen == 0 && !a.light_render && !b.shade) {
                 StageOp m = b;
-                m.shade_light = a.shade_light;
+                m.shade = a.shade; m.shade_lo = a.shade_lo; m.shade_hi = a.shade_hi;
                 a = m;
                 continue;
             }
@@ -975,8 +1088,9 @@ int ensureWaveBuffers(rt_render* r) {
     A((void**)&r->w_ray, sizeof(float4) * 2 * n);
     A((void**)&r->w_poi, sizeof(float4) * 2 * n);
     A((void**)&r->w_atte, sizeof(float4) * n);
-    A((void**)&r->w_sh, sizeof(float4) * 2 * n);
-    A((void**)&r->w_queue, sizeof(unsigned) * n);
+    const size_t nl = r->scene->lights.size() ? r->scene->lights.size() : 1;
+    A((void**)&r->w_sh, sizeof(float4) * 2 * n * nl);      // one shadow ray per light and slot
+    A((void**)&r->w_queue, sizeof(unsigned) * n * nl);     // any-hit walks queue (light, slot) entries
     A((void**)&r->w_qctr, sizeof(unsigned) * 2 * kMaxStages);
     return rc;
 }
@@ -989,7 +1103,7 @@ void launchStageT(rt_ctx* ctx, const SceneDev& sc, const PathArgs& a, const Wave
 }
 template <int GEN, bool LR, bool SHADE>
 void launchStage2(rt_ctx* ctx, const SceneDev& sc, const PathArgs& a, const WaveState& w, const StageOp& op, unsigned n) {
-    const bool shadow = op.shadow_light >= 0;
+    const bool shadow = op.shadow != 0;
     if (op.kind == 0) {
         if (shadow) launchStageT<GEN, LR, SHADE, true, 0>(ctx, sc, a, w, op, n); else launchStageT<GEN, LR, SHADE, false, 0>(ctx, sc, a, w, op, n);
     } else {
@@ -998,7 +1112,7 @@ void launchStage2(rt_ctx* ctx, const SceneDev& sc, const PathArgs& a, const Wave
 }
 template <int GEN>
 void launchStage1(rt_ctx* ctx, const SceneDev& sc, const PathArgs& a, const WaveState& w, const StageOp& op, unsigned n) {
-    const bool shade = op.shade_light >= 0;
+    const bool shade = op.shade != 0;
     if (op.light_render) {
         if (shade) launchStage2<GEN, true, true>(ctx, sc, a, w, op, n); else launchStage2<GEN, true, false>(ctx, sc, a, w, op, n);
     } else {
@@ -1032,7 +1146,7 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
             // a seed upload still in flight (rt_render_write_local_seeds_async) is waited for here, in front of the
             // first stage that draws random numbers: bouncePaths / initShadowTrace (initTrace only when rpp == 1,
             // and then rt_render_execute has waited already)
-            if (s.op.gen == 2 || s.op.shadow_light >= 0) RT_TRY_W(rt_seeds_ready(r));
+            if (s.op.gen == 2 || s.op.shadow) RT_TRY_W(rt_seeds_ready(r));
             RT_TRY_W(rt_time_mark(r, 0));
             launchStage(ctx, sc, a, w, s.op, n);
             RT_LAUNCH_CHECK(ctx, "wave_stage");

@@ -823,7 +823,7 @@ class Renderer:
                             "closest_queries": int(row[0]), "any_queries": int(row[8]),
                             "cells": int(row[2] + row[10]), "tests": int(row[3] + row[4] + row[11] + row[12])})
         return {"bytes_per_pass": int(c + a + stream), "traversal_bytes": int(c + a), "streaming_bytes": int(stream),
-                "profile": [int(v) for v in tot], "per_set": per_set}
+                "profile": [int(v) for v in tot], "per_set": per_set, "profile_sets": [[int(v) for v in row] for row in p]}
 
     # -- checkpoint / resume of the progressive state (acu, seeds, passes); the reference keeps it only on the device --
     def export_state(self):

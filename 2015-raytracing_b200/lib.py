@@ -79,6 +79,7 @@ _SIGS = {
     "rt_buffer_fill": ([P, P, I, Z], I),
     "rt_struct_size": ([C.c_char_p, I], U),
     "rt_set_walk_stats": ([P, P, P, P], I),
+    "rt_set_walk_totals": ([P, P], I),
     "rt_a10_initAcu": ([P, P, U], I),
     "rt_a10_initTrace": ([P, P, P, P, P, P, F, F, U], I),
     "rt_a10_bouncePaths": ([P, P, P, P, U], I),

@@ -51,8 +51,10 @@ def parse_args():
     ap.add_argument("--mode", type=int, default=0, help="0 fused (default), 1 reference kernel schedule")
     ap.add_argument("--tile-slots", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the compact configs 1-4 block (bench_configs.py) appended at N = 1")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the frame the CPU baseline renders (0 = auto)")
     ap.add_argument("--seed", type=int, default=2015)
+    ap.add_argument("--profile-passes", type=int, default=0, help="profiling aid (ncu): run this many passes of the workload and exit, no timing legs")
     return ap.parse_args()
 
 
@@ -69,7 +71,7 @@ def build_scene(rt, args, tmp):
 
     path = synth.write_scene(tmp, n_lights=args.lights, with_sphere=True, with_mesh=True, mesh_nslabs=args.nslabs)
     scene = rt.loadScene(path, args.cols, args.rows, mesh_loader=loader)
-    return scene
+    return scene, jmesh_holder.get("m")
 
 
 def workload_name(args):
@@ -171,10 +173,51 @@ def cpu_pass_rows(olib, prep, cam16, args, focal, lens_diam, rows, seed):
 
 
 # ------------------------------------------------------------------------------ roofline
-def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
-    """Roofline of the DOMINANT kernel: its ALGORITHMIC bytes (counted by the
-    instrumented pass on the same inputs, per geometry set) over its launch time measured with
-    CUDA events inside the timed region.  The whole step is reported next to it."""
+WALK_KERNEL = {"walk_triangle_closest": "k_walk_pairs<triangle, closest hit>", "walk_triangle_any": "k_walk_pairs<triangle, any hit>",
+               "walk_sphere_closest": "k_walk_pairs<sphere, closest hit>", "walk_sphere_any": "k_walk_pairs<sphere, any hit>"}
+NCU_WORKLOAD = (1920, 1080, 256, 5, 1000, 500, 128, 2)
+
+
+def load_ncu_classes(args, world):
+    """The committed ncu capture of ONE pass of this workload (profiles/*_ncu_classes.json, written by
+    profiles/ncu_classes.py): per kernel class the DRAM bytes and the warp / thread instructions of its launches.  Returned
+    only when it belongs to THIS build -- the file carries a hash of the kernel sources -- and to the default workload at
+    N = 1 (per-launch figures do not transfer to other tile sizes); otherwise (None, reason)."""
+    if (args.cols, args.rows, args.spp, args.depth, args.mesh_u, args.mesh_v, args.nslabs, args.lights) != NCU_WORKLOAD or args.mode != 0:
+        return None, "no ncu capture for a non-default workload"
+    if world != 1:
+        return None, "the ncu capture is per launch at N = 1 (one GPU, never a multi-rank command)"
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    try:
+        import ncu_classes
+        sha = ncu_classes.source_sha(ROOT)
+    except Exception as e:   # sources missing: cannot prove freshness
+        return None, "cannot hash the kernel sources (%s)" % e
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for fn in sorted(os.listdir(pdir)):
+        if fn.endswith("_ncu_classes.json"):
+            try:
+                d = json.load(open(os.path.join(pdir, fn)))
+            except Exception:
+                continue
+            if d.get("source_sha") == sha:
+                best = (fn, d)
+    if best is None:
+        return None, "stale: no profiles/*_ncu_classes.json was captured from the current kernel sources (sha %s)" % sha
+    return best, None
+
+
+def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak, world, clocks, info):
+    """Roofline of the DOMINANT kernel.  Three ceilings, all per launch of that kernel class:
+      frac       ALGORITHMIC bytes (the reference layout's bytes for the work done, counted by the instrumented
+                 pass on the same inputs, per geometry set) / launch time (CUDA events inside the timed region) / HBM peak;
+      frac_dram  MEASURED DRAM bytes (ncu dram__bytes_read + write of the same launches, from the committed capture of this
+                 build) / the same launch time / HBM peak;
+      issue      warp instructions issued / (SMs x 4 schedulers x clock x time), the lanes those instructions kept busy, and
+                 the share of the FP32 lanes doing the algorithm's own arithmetic (5 flops per face cull + 40 per full
+                 triangle test, 18 per sphere test).
+    `bound` names the ceiling the kernel sits closest to.  The whole step is reported next to it."""
     alg = r.algorithmic_bytes()
     walk = {k: v for k, v in tclass.items() if k.startswith("walk_") and v["launches"]}
     step_ms = kern_ms / max(args.steps, 1)
@@ -182,10 +225,11 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
             "achieved_gbs": round(alg["bytes_per_pass"] / (step_ms * 1e-3) / 1e9, 2),
             "class_ms_per_step": {k: round(v["ms"] / args.steps, 3) for k, v in tclass.items() if v["launches"]},
             "class_launches_per_step": {k: v["launches"] // args.steps for k, v in tclass.items() if v["launches"]}}
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if measured_peak else "fallback"
     if not walk:   # megakernel / reference schedule: the step is the kernel
         achieved = step["achieved_gbs"]
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
-                "kernel": "k_pathMega" if args.mode == 2 else "whole pass", "peak_source": "measured" if measured_peak else "fallback",
+                "kernel": "k_pathMega" if args.mode == 2 else "whole pass", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg["bytes_per_pass"], "launch_ms": round(step_ms, 3), "step": step}
     # heavy sets (the ones the queue walkers serve), by primitive kind; rows of the work profile are in set order
     kinds = []
@@ -195,50 +239,70 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak):
         kinds.append(("triangle", r._grids[len(kinds)]))
     for m in scene["meshes"]:
         kinds.append(("triangle", m.grid))
-    byts = {"walk_sphere_closest": 0, "walk_sphere_any": 0, "walk_triangle_closest": 0, "walk_triangle_any": 0}
-    for row, (kind, g) in zip(alg["per_set"], kinds):
+    byts = {k: 0 for k in WALK_KERNEL}
+    flops = {k: 0 for k in WALK_KERNEL}
+    prof = alg["profile_sets"]
+    for row, p, (kind, g) in zip(alg["per_set"], prof, kinds):
         if not g.n_slabs > 1:   # 1-cell sets are intersected inline by the stage kernels
             continue
         # the walker sees only rays that hit the set's AABB: take the ray loads of the others out
         byts["walk_%s_closest" % kind] += row["closest_bytes"] - 48 * (row["closest_queries"] - row["closest_walks"])
         byts["walk_%s_any" % kind] += row["any_bytes"] - 48 * (row["any_queries"] - row["any_walks"])
+        if kind == "triangle":   # 5 flops per cull, 40 more for the tests that pass it; the front count [15] covers both ray kinds
+            tc, ta = p[4], p[12]
+            front = p[15]
+            flops["walk_triangle_closest"] += 5 * tc + 40 * front * tc / max(tc + ta, 1)
+            flops["walk_triangle_any"] += 5 * ta + 40 * front * ta / max(tc + ta, 1)
+        else:
+            flops["walk_sphere_closest"] += 18 * p[3]
+            flops["walk_sphere_any"] += 18 * p[11]
+    ncu, ncu_why = load_ncu_classes(args, world)
+    clock_hz = 1e6 * float((clocks or {}).get("sm_mhz") or 1965.0)
+    sms = info["sm_count"]
     dom = max(walk, key=lambda k: walk[k]["ms"])
     per = {}
     for k, v in walk.items():
         n_l = v["launches"]
         b_launch = byts[k] * args.steps / n_l
         ms_launch = v["ms"] / n_l
-        per[k] = {"launches_per_step": n_l // args.steps, "launch_ms": round(ms_launch, 4), "algorithmic_bytes_per_launch": int(b_launch),
-                  "achieved_gbs": round(b_launch / (ms_launch * 1e-3) / 1e9, 2), "share_of_step": round(v["ms"] / kern_ms, 4)}
+        t = ms_launch * 1e-3
+        e = {"launches_per_step": n_l // args.steps, "launch_ms": round(ms_launch, 4), "algorithmic_bytes_per_launch": int(b_launch),
+             "achieved_gbs": round(b_launch / t / 1e9, 2), "frac": round(b_launch / t / 1e9 / peak, 4), "share_of_step": round(v["ms"] / kern_ms, 4),
+             "fp32_useful_frac": round(flops[k] * args.steps / n_l / (sms * 128 * clock_hz * t), 4)}
+        c = ncu[1]["classes"].get(k) if ncu else None
+        if c and c["launches"] == e["launches_per_step"]:
+            dram = (c["dram_read"] + c["dram_write"]) / c["launches"]
+            e.update({"traffic": int(dram), "frac_dram": round(dram / t / 1e9 / peak, 4),
+                      "warp_inst_per_launch": int(c["warp_inst"] / c["launches"]),
+                      "issue_frac": round(c["warp_inst"] / c["launches"] / (sms * 4 * clock_hz * t), 4),
+                      "lanes_per_inst": round(c["thread_inst"] / max(c["warp_inst"], 1), 2),
+                      "lane_frac": round(c["thread_inst"] / c["launches"] / (sms * 4 * 32 * clock_hz * t), 4)})
+        per[k] = e
     d = per[dom]
-    name = {"walk_triangle_closest": "k_walk_pairs<triangle, closest hit>", "walk_triangle_any": "k_walk_pairs<triangle, any hit>",
-            "walk_sphere_closest": "k_walk_pairs<sphere, closest hit>", "walk_sphere_any": "k_walk_pairs<sphere, any hit>"}[dom]
-    return {"bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": round(d["achieved_gbs"] / peak, 4),
-            "traffic": ncu_traffic(dom, args, d["launches_per_step"]),
-            "kernel": name, "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if measured_peak else "fallback",
-            "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "launch_ms": d["launch_ms"],
-            "share_of_step": d["share_of_step"], "kernels": per, "step": step,
-            "work_per_set": alg["per_set"][:len(kinds)]}
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the walker kernels from the committed `ncu --set full`
-# capture of this command at N = 1 (profiles/r1d_walk_full_summary.md, mean over the captured launches).  A launch
-# walks the queue of ONE tile of ONE pipeline stage; at N = 1 the frame is two tiles (412 721 664 + 118 119 936 slots =
-# a quarter of device memory + the rest) and the captured launches belong to the SMALL tile, so the figure is per
-# 118 119 936 slots.  Traffic follows the number of queued rays, hence the slots: a step's total is the figure x
-# (slots of this rank / 118 119 936) x stages (any hit: (1 + depth) x lights, closest hit: 1 + depth), divided over
-# the launches of the step for the per-launch average reported next to `achieved`.  Default workload only.
-NCU_TRAFFIC = {"walk_triangle_any": 22458861576, "walk_triangle_closest": 22251870372}
-NCU_TRAFFIC_SLOTS = 118119936
-NCU_TRAFFIC_WORKLOAD = (1920, 1080, 256, 1000, 500, 128, 2)
-
-
-def ncu_traffic(dom, args, launches_per_step):
-    if dom not in NCU_TRAFFIC or (args.cols, args.rows, args.spp, args.mesh_u, args.mesh_v, args.nslabs, args.lights) != NCU_TRAFFIC_WORKLOAD:
-        return None
-    stages = (1 + args.depth) * (args.lights if dom.endswith("_any") else 1)
-    slots = args.cols * args.rows * args.spp / max(args.gpus, 1)
-    return int(NCU_TRAFFIC[dom] * (slots / NCU_TRAFFIC_SLOTS) * stages / max(launches_per_step, 1))
+    # which ceiling is the kernel closest to?  (issue slots vs measured DRAM traffic; the algorithmic rate is a contract figure)
+    bound = "hbm"
+    if "issue_frac" in d and d["issue_frac"] > d.get("frac_dram", 0.0):
+        bound = "issue"
+    out = {"bound": bound, "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": d["frac"],
+           "traffic": d.get("traffic"), "frac_dram": d.get("frac_dram"),
+           "kernel": WALK_KERNEL[dom], "peak_source": peak_src,
+           "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "launch_ms": d["launch_ms"],
+           "share_of_step": d["share_of_step"],
+           "issue": {k: d.get(k) for k in ("issue_frac", "lanes_per_inst", "lane_frac", "fp32_useful_frac", "warp_inst_per_launch")},
+           "issue_peak": "%d SMs x 4 schedulers x 1 warp instruction per cycle at %.0f MHz (median SM clock sampled during the timed region); "
+                         "fp32_useful_frac = algorithmic FP32 operations / (%d SMs x 128 lanes x clock x time)" % (sms, clock_hz / 1e6, sms),
+           "ncu_profile": ncu[0] if ncu else None, "ncu_profile_note": ncu_why,
+           "kernels": per, "step": step, "work_per_set": alg["per_set"][:len(kinds)]}
+    if ncu and "stage" in ncu[1]["classes"] and tclass.get("stage", {}).get("launches"):
+        c, v = ncu[1]["classes"]["stage"], tclass["stage"]
+        if c["launches"] == v["launches"] // args.steps:
+            t = v["ms"] / args.steps * 1e-3
+            out["stage"] = {"launches_per_step": c["launches"], "ms_per_step": round(v["ms"] / args.steps, 3),
+                            "traffic_per_step": int(c["dram_read"] + c["dram_write"]),
+                            "frac_dram": round((c["dram_read"] + c["dram_write"]) / t / 1e9 / peak, 4),
+                            "issue_frac": round(c["warp_inst"] / (sms * 4 * clock_hz * t), 4),
+                            "lanes_per_inst": round(c["thread_inst"] / max(c["warp_inst"], 1), 2)}
+    return out
 
 
 # ------------------------------------------------------------------------------ main
@@ -265,7 +329,7 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
 
     tmp = tempfile.mkdtemp(prefix="rt_bench_")
-    scene = build_scene(rt, args, tmp)
+    scene, mesh_data = build_scene(rt, args, tmp)
     slot_begin, slots_pp = rt.multi.slot_range(rank, world, args.spp)   # split by samples per pixel
     r = rt.Renderer(scene, args.cols, args.rows, args.spp, depth=args.depth, device=local_rank, slots=(slot_begin, slots_pp),
                     mode=args.mode, tile_slots=args.tile_slots)
@@ -341,6 +405,16 @@ def main():
         return ms, rays, launches, kern_ms
 
     set_seeds_local()
+    if args.profile_passes:   # under ncu: only the kernels of these passes, then the same orderly exit
+        for _ in range(args.profile_passes):
+            step_device()
+        del ext
+        ctx.finish()
+        if comm is not None:
+            comm.close()
+        ctx.free(pix_dev)
+        r.postRender()
+        return
     for _ in range(args.warmup):
         step_device()
     sampler = ClockSampler(local_rank)
@@ -370,7 +444,7 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        roofline = roofline_of(r, scene, tclass, kern_ms, args, peak, bool(peaks))
+        roofline = roofline_of(r, scene, tclass, kern_ms, args, peak, bool(peaks), world, clocks, info)
         cpu = None
         if not args.no_cpu_baseline and world == 1:   # reported at N = 1 only
             cpu = cpu_baseline(args)
@@ -409,6 +483,20 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and world == 1 and not args.no_configs and not args.no_cpu_baseline:
+        # BASELINE.json configs 1-4 in compact form (one named input each, GPU side only, ~15 s): ms/frame + roofline fraction,
+        # so that the driver's record carries them; `python bench_configs.py` is the full list with the CPU leg
+        try:
+            import bench_configs
+            ctx2 = rt.lib.Context(local_rank)
+            try:
+                big = mesh_data if (args.mesh_u, args.mesh_v) == (1000, 500) else None
+                out["configs"] = bench_configs.run_configs(rt, ctx2, compact=True, with_cpu=False, reps=2, big_mesh=big,
+                                                           hbm_peak=float(out["roofline"]["peak"]))
+            finally:
+                ctx2.close()
+        except Exception as e:   # supplementary block: never lose the headline line over it
+            out["configs"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out))
     sys.stdout.flush()

@@ -173,12 +173,18 @@ typedef struct {
 int rt_a089_render_frame(rt_ctx*, const rt_a089_frame* frame, void* acu, void* out_matid, void* out_maxt);
 
 /* Optional per-work-item statistics for the grid-walk launchers -- the five of Assignment 10 (sphereTrace,
- * triangleTrace, meshTrace, sphereShadowTrace, triangleShadowTrace) and molTrace / meshTrace of Assignment 7 (all
+ * triangleTrace, meshTrace, sphereShadowTrace, triangleShadowTrace), their Assignment 8 / 9 twins and molTrace /
+ * meshTrace of Assignment 7 (all
  * device pointers, one uint per work-item, any may be NULL; pass all NULL to switch off): winning reference index
  * champ_i (0xFFFFFFFF = none; A10/code.cl:882-897), cells visited, primitive tests.  Used for the hit-primitive-id
  * parity gate and for the algorithmic byte count of the roofline.  With occupancy bits present the
  * walk skips the table loads of empty cells but still counts them as visited, like the reference's loop. */
 int rt_set_walk_stats(rt_ctx*, void* hit_id_u32, void* cells_u32, void* tests_u32);
+/* The same counters as running totals over every grid-walk launch until switched off (NULL): a device array of 8 x uint64
+ * the launches ADD to -- [0] rays that entered a walk kernel alive (mint != maxt), [1] of those, walks started (the set's box was
+ * hit), [2] cells visited, [3] primitive tests, [4] hits, [5] triangle tests that passed the face cull; [6], [7] reserved.
+ * Feeds the algorithmic byte count 48 + 8 C + B T + H (...) per ray of BASELINE.md section 3 for configs 3 and 4. */
+int rt_set_walk_totals(rt_ctx*, void* totals_u64x8);
 
 /* ---- 3. grid build, scene, render ---------------------------------------------------------
  * Uniform-grid build = splitSphereData / splitTriangleData / splitMeshData
@@ -330,7 +336,8 @@ int rt_render_stats(rt_render*, unsigned long long* closest_rays, unsigned long 
  *   [2] cells visited   [3] sphere tests   [4] triangle tests
  *   [5] hits on sphere sets   [6] hits on triangle sets with a matid array   [7] hits on meshes
  *   [8] any-hit (ray,set) queries entered alive   [9] walks started   [10] cells   [11] sphere tests
- *   [12] triangle tests   [13] blocked   [14] slots processed   [15] reserved
+ *   [12] triangle tests   [13] blocked   [14] slots processed
+ *   [15] triangle tests (closest + any hit) that pass the face cull and run the full barycentric test
  * Timing taken with the profile on is not a benchmark number. */
 int rt_render_set_profile(rt_render*, int on);
 int rt_render_read_profile(rt_render*, unsigned long long out[16]);

@@ -490,3 +490,80 @@ def test_non_blocking_seed_upload_is_equivalent(rt, scenes, mode, rpp):
         out.append(res)
     for (p0, a0, s0), (p1, a1, s1) in zip(*out):
         assert np.array_equal(s0, s1) and np.array_equal(a0.view(np.uint32), a1.view(np.uint32)) and np.array_equal(p0, p1)
+
+
+def test_nccl_reduce_from_the_library(rt, scenes):
+    """rt_comm_* / rt_render_reduce: the accumulation image is reduced by an ncclReduce the C library issues on the context's
+    stream (libnccl bound at run time).  One GPU here, so a communicator of one rank: the call path (dlopen, unique id, init,
+    reduce on the render stream, destroy) runs for real and must leave the image untouched; the N > 1 sum is covered by the
+    2/4/8-GPU bench runs and, for the split / merge logic, by tests/test_multi_gloo.py."""
+    _, p_scene = scenes
+    r = rt.Renderer(p_scene, COLS, ROWS, RPP)
+    r.preRender(OR.make_seeds(COLS * ROWS * RPP, 5))
+    comm = None
+    try:
+        r.executeRender()
+        before = r.accum()
+        comm = rt.multi.Comm(r.ctx, 0, 1, exchange=lambda ident: ident)
+        comm.reduce(r, 0)
+        r.ctx.finish()
+        assert np.array_equal(r.accum().view(np.uint32), before.view(np.uint32))
+        with pytest.raises(rt.lib.RtError):
+            comm.reduce(r, 3)   # root outside the communicator
+    finally:
+        if comm is not None:
+            comm.close()
+        r.postRender()
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_caller_built_grids_without_occupancy_bits(rt, scenes, monkeypatch, mode):
+    """The drop-in ABI accepts grids the CALLER built (any box_size / prim buffers; `occupancy` is an internal extra of the
+    library's own builder).  Multi-cell grids that arrive without occupancy bits get them derived from the cell table in
+    rt_scene_add_set; the frame must equal the one rendered from the library-built grids (global n_slabs 3: sphere and
+    triangle sets are multi-cell too, next to the mesh)."""
+    _, p_scene = scenes
+    seeds0 = OR.make_seeds(COLS * ROWS * RPP, 77)
+
+    def frame():
+        r = rt.Renderer(p_scene, COLS, ROWS, RPP, n_slabs=3, mode=mode)
+        r.preRender(seeds0)
+        try:
+            r.executeRender()
+            return r.accum(), r.seeds()
+        finally:
+            r.postRender()
+
+    want_acc, want_seeds = frame()
+    real = rt.lib.dll.rt_scene_add_set
+    stripped = []
+
+    def add_set_without_occupancy(hs, grid_ref, bound, is_mesh, matid):
+        g = grid_ref._obj
+        assert g.n_slabs > 1 and g.occupancy
+        bare = rt.lib.Grid.from_buffer_copy(bytes(g))
+        bare.occupancy = None
+        stripped.append(bare)
+        return real(hs, C.byref(bare), bound, is_mesh, matid)
+
+    monkeypatch.setattr(rt.lib.dll, "rt_scene_add_set", add_set_without_occupancy, raising=False)
+    got_acc, got_seeds = frame()
+    assert len(stripped) == 3
+    assert np.array_equal(got_seeds, want_seeds)
+    assert np.array_equal(got_acc.view(np.uint32), want_acc.view(np.uint32))
+
+
+def test_empty_slot_range_is_rejected(rt, scenes, gpu_ctx):
+    """multi.slot_range hands (begin, 0) to ranks beyond rays_per_pixel; such a rank must not silently render EVERY slot
+    (slot_count 0 used to mean "all"): the Python layer and the C ABI both refuse."""
+    _, p_scene = scenes
+    assert rt.multi.slot_range(5, 8, 4) == (4, 0)
+    with pytest.raises(ValueError, match="empty slot range"):
+        rt.Renderer(p_scene, COLS, ROWS, 4, slots=(4, 0), ctx=gpu_ctx)
+    r = rt.Renderer(p_scene, COLS, ROWS, 4, ctx=gpu_ctx)
+    r.slots = (2, 0)   # past the Python check, straight to rt_render_create
+    with pytest.raises(rt.lib.RtError, match="empty slot range"):
+        try:
+            r.preRender(None)
+        finally:
+            r.postRender()
