@@ -6,6 +6,8 @@
 // rt_render_create: the queue walkers want deep queues, the state streams through HBM either way);
 // only the per-slot seed and accumulation buffers persist across passes, exactly as in the
 // reference (acu is never cleared between passes, A10/code.js:1078-1099).
+#include <math.h>
+
 #include "rt_frame.h"
 
 using namespace rt;
@@ -248,6 +250,7 @@ int rt_scene_destroy(rt_scene* s) {
         if (st.pre_pe) rt_buffer_release(s->ctx, st.pre_pe);
         if (st.macro_occ) rt_buffer_release(s->ctx, st.macro_occ);
         if (st.own_occ) rt_buffer_release(s->ctx, st.own_occ);
+        if (st.macro_dist) rt_buffer_release(s->ctx, st.macro_dist);
     }
     delete s;
     return RT_OK;
@@ -299,6 +302,87 @@ int rt_scene_add_set(rt_scene* s, const rt_grid* grid, const float bound[8], int
         f_macroOccupancy<<<rt_blocks((mcells + 31) / 32 * 32, kBlock), kBlock, 0, ctx->stream>>>((const unsigned*)grid->occupancy, grid->n_slabs, sh,
                                                                                                  st.macro_n, st.macro_occ);
         RT_LAUNCH_CHECK(ctx, "macroOccupancy");
+        // Distance field for the empty-walk proof (rt_wavefront.cu): chessboard (L-infinity) distance of every cell of a
+        // <= 128^3 grid (the fine cells themselves up to n = 128, 2 x 2 x 2 blocks up to 256, ...) to the nearest occupied one, on
+        // the host: two raster passes with the 13 already-visited neighbours each are exact for this metric.
+        unsigned dsh = 0;
+        while (((grid->n_slabs + (1u << dsh) - 1) >> dsh) > 128) dsh++;
+        const int nd = (int)((grid->n_slabs + (1u << dsh) - 1) >> dsh);
+        const size_t dcells = (size_t)nd * nd * nd, fine = (size_t)grid->n_slabs * grid->n_slabs * grid->n_slabs;
+        std::vector<unsigned> occ((fine + 31) / 32);
+        RT_TRY(rt_buffer_read(ctx, grid->occupancy, 0, sizeof(unsigned) * occ.size(), occ.data()));
+        std::vector<unsigned char> dist(dcells, 255);
+        {
+            const unsigned nn = grid->n_slabs;
+            for (size_t w = 0; w < occ.size(); w++) {
+                unsigned bits = occ[w];
+                while (bits) {
+                    const size_t c = w * 32 + (size_t)(__builtin_ctz(bits));
+                    bits &= bits - 1;
+                    if (c >= fine) break;
+                    const unsigned x = (unsigned)(c % nn), y = (unsigned)((c / nn) % nn), z = (unsigned)(c / ((size_t)nn * nn));
+                    dist[((size_t)(z >> dsh) * nd + (y >> dsh)) * nd + (x >> dsh)] = 0;
+                }
+            }
+        }
+        auto at = [&](int z, int y, int x) -> unsigned char& { return dist[((size_t)z * nd + y) * nd + x]; };
+        for (int pass = 0; pass < 2; pass++) {
+            const int lo = pass ? nd - 1 : 0, hi = pass ? -1 : nd, dir = pass ? -1 : 1;
+            for (int z = lo; z != hi; z += dir)
+                for (int y = lo; y != hi; y += dir)
+                    for (int x = lo; x != hi; x += dir) {
+                        unsigned best = at(z, y, x);
+                        if (best == 0) continue;
+                        for (int dz = -1; dz <= 0; dz++)
+                            for (int dy = -1; dy <= (dz < 0 ? 1 : 0); dy++)
+                                for (int dx = -1; dx <= ((dz < 0 || dy < 0) ? 1 : -1); dx++) {
+                                    const int zz = z + dir * dz, yy = y + dir * dy, xx = x + dir * dx;
+                                    if (zz < 0 || yy < 0 || xx < 0 || zz >= nd || yy >= nd || xx >= nd) continue;
+                                    const unsigned v = at(zz, yy, xx) + 1u;
+                                    if (v < best) best = v;
+                                }
+                        at(z, y, x) = (unsigned char)(best > 255 ? 255 : best);
+                    }
+        }
+        RT_TRY(rt_buffer_create(ctx, dcells, (void**)&st.macro_dist));
+        RT_TRY(rt_buffer_write(ctx, st.macro_dist, 0, dcells, dist.data()));
+        st.dist_shift = dsh;
+        st.dist_n = (unsigned)nd;
+        const float fcell = (float)(1u << dsh), nf = (float)grid->n_slabs;
+        for (int a = 0; a < 3; a++) st.dist_inv[a] = nf / ((bound[4 + a] - bound[a]) * fcell);
+    }
+    if (grid->kind == 1 && grid->n_slabs == 1 && grid->n_refs > 0 && grid->n_refs <= 4096) {
+        // "walls": every triangle planar in one coordinate (three equal fp32 values) and not a sliver -> the room between the planes
+        rt_ctx* ctx = s->ctx;
+        std::vector<float> tp((size_t)grid->n_refs * 12);
+        RT_TRY(rt_buffer_read(ctx, grid->prim, 0, sizeof(float) * tp.size(), tp.data()));
+        const float inf = __builtin_inff();
+        float lo[3] = {-inf, -inf, -inf}, hi[3] = {inf, inf, inf}, scale = 0.f;
+        const float mid[3] = {0.5f * (bound[0] + bound[4]), 0.5f * (bound[1] + bound[5]), 0.5f * (bound[2] + bound[6])};
+        bool ok = true;
+        for (unsigned r = 0; r < grid->n_refs && ok; r++) {
+            const float* p0 = &tp[(size_t)r * 12];
+            const float* p1 = p0 + 4;
+            const float* p2 = p0 + 8;
+            int axis = -1;
+            for (int a = 0; a < 3; a++) if (p0[a] == p1[a] && p1[a] == p2[a]) axis = a;
+            if (axis < 0) { ok = false; break; }
+            double e1[3], e2[3], n[3];
+            for (int a = 0; a < 3; a++) { e1[a] = (double)p1[a] - p0[a]; e2[a] = (double)p2[a] - p0[a]; }
+            n[0] = e1[1] * e2[2] - e1[2] * e2[1]; n[1] = e1[2] * e2[0] - e1[0] * e2[2]; n[2] = e1[0] * e2[1] - e1[1] * e2[0];
+            const double l1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]), l2 = sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+            const double ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            if (!(ln >= 0.25 * l1 * l2) || !(ln > 0)) { ok = false; break; }   // sin of the angle at p0 >= 0.25, finite
+            const float c = p0[axis];
+            if (c <= mid[axis]) lo[axis] = lo[axis] > c ? lo[axis] : c; else hi[axis] = hi[axis] < c ? hi[axis] : c;
+            for (int k = 0; k < 3; k++) for (int a = 0; a < 3; a++) { const float m = fabsf(p0[4 * k + a]); if (m > scale) scale = m; }
+        }
+        for (int a = 0; a < 8 && ok; a++) if (a != 3 && a != 7) { const float m = fabsf(bound[a]); if (m > scale) scale = m; }
+        if (ok && scale > 0.f && scale < 1e30f) {
+            st.wall_ok = 1;
+            for (int a = 0; a < 3; a++) { st.wall_lo[a] = lo[a]; st.wall_hi[a] = hi[a]; }
+            st.wall_scale = scale;
+        }
     }
     if (grid->kind == 1 && grid->n_refs > 0) {   // every triangle set: precomputed face vector / edges (queue walkers and 1-cell sets)
         rt_ctx* ctx = s->ctx;
@@ -344,11 +428,11 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     r->local_slots = r->pixels * r->slots_pp;
     if ((unsigned long long)r->pixels * r->o.rays_per_pixel > 0xFFFFFFFFull) { delete r; return rt_fail(ctx, RT_ERR_INVALID, "render: total_rays exceeds the reference's uint range"); }
     // default tile: as many slots as a quarter of the device memory holds (wavefront state per slot: ray 32 + hit 32 +
-    // throughput 16 bytes, and per light a 32-byte shadow ray and a 4-byte queue entry; 180 GB of HBM3e on B200 -> ~300 Mi
+    // throughput 16 bytes, and per light a 32-byte shadow ray and two 4-byte queue entries; 180 GB of HBM3e on B200 -> ~300 Mi
     // slots with two lights): the persistent queue walkers need a DEEP queue -- with 4 Mi-slot tiles a walk launch got
     // ~0.5 M rays for 151 k lanes and spent a quarter of its time in the drain tail
     const size_t nlq = scene->lights.size() ? scene->lights.size() : 1;
-    const size_t slot_bytes = 80 + 36 * nlq;
+    const size_t slot_bytes = 80 + 40 * nlq;   // + a second (filtered) queue entry per light
     size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)(ctx->prop.totalGlobalMem / 4 / slot_bytes);
     if (want < ((size_t)1 << 22)) want = (size_t)1 << 22;
     if (want * nlq > 0xFFFFFFFFull) want = 0xFFFFFFFFull / nlq;   // queue entries are light * tile_slots + slot in 32 bits
@@ -389,7 +473,7 @@ int rt_render_destroy(rt_render* r) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* bufs[] = {r->seeds, r->acu, r->accum, r->pixel, r->rpp1_coords, r->rays, r->pois, r->shadow, r->d_counters, r->d_profile,
-                    r->w_ray, r->w_poi, r->w_atte, r->w_sh, r->w_queue, r->w_qctr};
+                    r->w_ray, r->w_poi, r->w_atte, r->w_sh, r->w_queue, r->w_qctr, r->w_queue_f, r->w_masks};
     for (void* b : bufs) if (b) cudaFree(b);
     if (r->copy_stream) { cudaStreamSynchronize(r->copy_stream); cudaStreamDestroy(r->copy_stream); }
     if (r->ev_seeds) cudaEventDestroy(r->ev_seeds);

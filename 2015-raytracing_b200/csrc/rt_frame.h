@@ -18,6 +18,15 @@ struct SceneSet {
     // small enough to sit in shared memory of the queue walkers (the fine bitmap is n^3 bits)
     unsigned* macro_occ = nullptr;
     unsigned macro_shift = 0, macro_n = 0;
+    // internal: chessboard distance (in field cells, capped at 255) from every cell of a <= 128^3 field to the nearest occupied one --
+    // lets the stage kernels PROVE that a ray's whole walk crosses empty cells only and skip the walk (rt_wavefront.cu)
+    unsigned char* macro_dist = nullptr;
+    float dist_inv[3] = {0.f, 0.f, 0.f};   // world -> distance-field index scale per axis
+    unsigned dist_shift = 0, dist_n = 0;   // the field has dist_n^3 cells of (2^dist_shift)^3 grid cells each (dist_n <= 128)
+    // internal, 1-cell triangle sets whose triangles are all axis-aligned and planar (the walls of a room): the open box between
+    // those planes around the set's centre -- shadow segments inside it are not tested against the set (rt_wavefront.cu)
+    int wall_ok = 0;
+    float wall_lo[3] = {0.f, 0.f, 0.f}, wall_hi[3] = {0.f, 0.f, 0.f}, wall_scale = 0.f;
     unsigned* own_occ = nullptr;   // occupancy bits derived here for a caller-built grid that came without (rt_scene_add_set)
 };
 struct SceneLight { float shadow[16], scene[16], light[16]; };
@@ -61,7 +70,9 @@ struct rt_render {
     float4* w_atte = nullptr;        // [n]
     float4* w_sh = nullptr;          // [2*n]: shadow ray (o.xyz, mint) (d.xyz, maxt)
     unsigned* w_queue = nullptr;     // [n] slot ids of the current heavy-set walk
-    unsigned* w_qctr = nullptr;      // [2*kMaxStages]: per walk stage {count, head}
+    unsigned* w_qctr = nullptr;      // [4*kMaxStages]: per walk stage {count, head}, as pushed and as filtered
+    unsigned* w_queue_f = nullptr;   // [n * lights] the queue after the filter (empty-walk proof)
+    unsigned* w_masks = nullptr;     // [n * lights / 32] the filter's keep bits
     // stats
     unsigned long long* d_counters = nullptr;   // [0] closest rays, [1] any rays
     unsigned long long* d_profile = nullptr;    // [RT_MAX_SETS][16] work counters per geometry set (rt_render_read_profile*)

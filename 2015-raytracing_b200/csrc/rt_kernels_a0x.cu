@@ -800,8 +800,8 @@ void launchA089Any(rt_ctx* ctx, unsigned total, void* shadow_rays, const GridVie
 
 template <int PRIM>
 void launchA07(rt_ctx* ctx, size_t n, void* pixels, const float* fcam, void* rays, const GridView& g, const void* normals) {
-    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests};
-    const bool stats = sp.hit || sp.cells || sp.tests;
+    StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests, ctx->st_totals};
+    const bool stats = sp.hit || sp.cells || sp.tests || sp.totals;
     if (stats) {
         if (g.occ) k_a07_trace<PRIM, true, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)normals, sp);
         else k_a07_trace<PRIM, false, true><<<RT_GRID1(n)>>>((uchar4*)pixels, mkCam(fcam), (Ray*)rays, g, (const float4*)normals, sp);

@@ -31,6 +31,11 @@ struct SetDev {
     const unsigned* macro_occ; // heavy sets: coarse occupancy (<= 64^3 bits)
     unsigned macro_shift, macro_n;
     int far_ok;                // 1-cell sets: the cell's exit planes are bit for bit the box's far planes (see farPlanesShared)
+    const unsigned char* macro_dist;   // heavy sets: chessboard distance of every cell of the distance field to the nearest occupied one (or null)
+    float dist_inv[3];         // world -> field-index scale per axis
+    unsigned dist_shift, dist_n;       // field cells are (2^dist_shift)^3 grid cells, dist_n per axis
+    int wall_ok;               // 1-cell triangle sets made of axis-aligned planar triangles ("walls"): see shadowClearsWalls
+    float wall_lo[3], wall_hi[3], wall_scale;
 };
 struct LightDev { LightArg shadow, scene, light; };
 struct SceneDev {
@@ -310,6 +315,18 @@ bool farPlanesShared(const float* b8) {
     return true;
 }
 
+// RT2015_NO_SKIP=1 (environment, read once) switches the empty-walk proof off (A/B runs; results are identical either way).
+bool skipEmptyWalks() {
+    static const bool v = !(getenv("RT2015_NO_SKIP") && atoi(getenv("RT2015_NO_SKIP")) != 0);
+    return v;
+}
+
+// RT2015_NO_WALL_SKIP=1 (environment, read once) switches shadowClearsWalls off (A/B runs; results are identical either way).
+bool skipWallTests() {
+    static const bool v = !(getenv("RT2015_NO_WALL_SKIP") && atoi(getenv("RT2015_NO_WALL_SKIP")) != 0);
+    return v;
+}
+
 int buildSceneDev(rt_render* r, SceneDev& sc) {
     rt_scene* s = r->scene;
     if ((int)s->sets.size() > kMaxSets || (int)s->lights.size() > kMaxLights)
@@ -337,6 +354,13 @@ int buildSceneDev(rt_render* r, SceneDev& sc) {
         d.macro_shift = in.macro_shift;
         d.macro_n = in.macro_n;
         d.far_ok = (RT_FAR_SHARE && in.grid.n_slabs == 1 && farPlanesShared(in.bound)) ? 1 : 0;
+        d.macro_dist = skipEmptyWalks() ? in.macro_dist : nullptr;
+        for (int a = 0; a < 3; a++) d.dist_inv[a] = in.dist_inv[a];
+        d.dist_shift = in.dist_shift;
+        d.dist_n = in.dist_n;
+        d.wall_ok = (in.wall_ok && skipWallTests()) ? 1 : 0;
+        for (int a = 0; a < 3; a++) { d.wall_lo[a] = in.wall_lo[a]; d.wall_hi[a] = in.wall_hi[a]; }
+        d.wall_scale = in.wall_scale;
     }
     for (int i = 0; i < sc.n_lights; i++) {
         memcpy(sc.lights[i].shadow.v, s->lights[i].shadow, 64);
@@ -393,6 +417,42 @@ struct StageOp {
     int light_lo, light_hi;   // lights whose shadow rays this stage generates / traces (kind 1)
 };
 
+// ---------------------------------------------------------------------------------------
+// Shadow rays against a room.  Two thirds of all inline triangle tests of a path-traced pass are shadow rays tested
+// against the walls of the room they live in (12 triangles x lights x 6 segments per slot) -- and a segment between two
+// points INSIDE a room cannot hit its walls.  When a 1-cell triangle set consists of axis-aligned planar triangles only,
+// the host derives the open box between those planes that contains the set's centre (rt_scene_add_set); a shadow
+// segment whose origin and end point both lie inside that box -- with margins that dominate the rounding of the
+// reference's test -- is rejected by every triangle of the set in the reference too, so the whole set is skipped for it.
+// Why the reference rejects (A10/code.cl:250-288, t = dot(cross(s, e2), e1) / -div): for a triangle in the plane x_a = c the
+// exact parameter is t* = h / v with h = c - o_a the origin's distance to the plane and v = d_a; the computed t carries a
+// relative error E <= 6e-7 (|s| / (h sin(theta)) + 1 / |v|) (10 roundings of 2^-24 in the triple product and in div; theta =
+// angle at p0, >= 14.5 degrees required on the host).  (i) Plane behind or at the origin side, h v < 0: t* < 0 and stays
+// negative for E < 1, guaranteed by h >= 2e-5 scale -- or, once |v| is so small that the sign of div is in doubt, |t| >= h
+// / |v| exceeds any segment length.  (ii) Plane beyond the end point by g: t* - maxt = g / |v| and t* <= 2 scale / |v|, so
+// (t* - maxt) / t* >= g / (2 scale) must exceed E <= 8.4e-6 scale / g + 6e-7 / |v| (h >= g, |s| <= 3.5 scale): required with a
+// factor 6 to spare as g >= 1e-2 scale and g |v| >= 4e-6 scale.  In both cases
+// `t < champ_t = maxt` or `t >= mint >= 0` fails, whatever beta and gamma are.  Checked against the reference kernels on
+// adversarial shadow rays (tests/test_gpu_gates.py); RT2015_NO_WALL_SKIP=1 switches it off.
+// ---------------------------------------------------------------------------------------
+RT_DEV bool shadowClearsWalls(const SetDev& s, const RayR& sr) {
+    if (!(sr.maxt < RT_INF)) return false;
+    const float sc = s.wall_scale;
+    const float o[3] = {sr.o.x, sr.o.y, sr.o.z}, d[3] = {sr.d.x, sr.d.y, sr.d.z};
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float q = o[a] + sr.maxt * d[a];            // end point of the segment
+        const float v = fabsf(d[a]);
+        // origin strictly inside, by more than the rounding of its own distance to either plane
+        ok = ok && (o[a] - s.wall_lo[a] >= 2e-5f * sc) && (s.wall_hi[a] - o[a] >= 2e-5f * sc);
+        // end point inside with a margin that grows as the ray gets parallel to the plane
+        const float g = fminf(q - s.wall_lo[a], s.wall_hi[a] - q);
+        ok = ok && (g >= 1e-2f * sc) && (g * v >= 4e-6f * sc);
+    }
+    return ok;   // NaNs anywhere fail the comparisons
+}
+
 // Loads / stores of the per-slot wavefront state (rays, hit records, shadow rays, queues, seeds, accumulators): every
 // byte is touched once per kernel and the tile is gigabytes, so nothing of it survives in the L2 until the next kernel
 // anyway.  RT_STREAM_CS = 1 marks these accesses evict-first (ld/st.global.cs) so that they stop displacing the scene data
@@ -413,6 +473,50 @@ template <class T> RT_DEV void stS(T* p, T v) {
 #else
     *p = v;
 #endif
+}
+
+// ---------------------------------------------------------------------------------------
+// Empty-walk proof.  A third of the rays that enter a heavy set's box cross EMPTY cells only (they cut the corners of
+// the box around a mesh) and account for almost half of all cell steps (instrumented oracle, config 5: 34 % of the walks,
+// 45-49 % of the cells).  Such a walk tests nothing and changes nothing, so it may be skipped -- if that can be PROVEN
+// without doing it.  The proof marches the exact ray through a distance field of the occupancy grid (the grid's own cells
+// up to n = 128, blocks of 2^k cells above): dist[c] = D says every field cell closer than D (chessboard metric) to c is empty,
+// so from a point in c the ray may advance D - 3.5 field cells and every cell within 2 field cells of that stretch is still empty.  The 2 is the safety margin
+// for the difference between the exact ray and the cells the reference's fp32 DDA (A10/code.cl:694-786) really visits:
+// its entry slab is one division + truncation (<= 1 fine cell off), its per-axis crossing times are the exact first
+// crossing plus up to n fp32 additions (relative error 2^-24 each) -- bounded below per ray by `e` fine cells and
+// required to be <= 1 -- so it stays within 2 fine cells (<= 2 field cells) of the exact ray; 1.5 more field cells
+// cover point-to-cell quantisation and the rounding of this march itself.  Rays with a zero / non-finite direction
+// component or a non-finite box interval (where the reference's float-equality stepping degenerates, quirk Q12) are
+// never skipped.  A skipped ray is exactly a ray whose walk would have visited no reference: checked against the
+// instrumented reference kernels on millions of random and adversarial rays (tests/test_gpu_gates.py).
+// Where it runs: NOT in the per-slot stage kernels -- only ~13 % of the slots of a stage hit the heavy set's box, so a
+// warp there pays its slowest lane's march for 4 useful lanes (measured: stage 606 -> 724 ms, more than the walkers
+// gained) -- but in k_filter_mark, a pass over the compact queue between stage and walk where every lane has a ray to prove.
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxMarch = 32;
+RT_DEV bool walkProvablyEmpty(f3 o, f3 d, float tmin, float tmax, const SetDev& s) {
+    const unsigned char* dist = s.macro_dist;
+    if (!dist) return false;
+    const f3 du = mk3(d.x * s.dist_inv[0], d.y * s.dist_inv[1], d.z * s.dist_inv[2]);   // coarse cells per unit t
+    const float dmax = fmaxf(fmaxf(fabsf(du.x), fabsf(du.y)), fabsf(du.z));
+    if (d.x == 0.0f || d.y == 0.0f || d.z == 0.0f || !(dmax < RT_INF) || !(tmin >= 0.0f) || !(tmax < RT_INF)) return false;
+    const float fcell = (float)(1u << s.dist_shift);
+    const float e = (float)s.g.n * 1.2e-7f * tmax * dmax * fcell;   // drift bound of the reference's t_next sequences, in fine cells
+    if (!(e <= 1.0f)) return false;
+    const f3 u0 = mk3((o.x - s.g.bound.pmin.x) * s.dist_inv[0], (o.y - s.g.bound.pmin.y) * s.dist_inv[1], (o.z - s.g.bound.pmin.z) * s.dist_inv[2]);
+    const float rd = 1.0f / dmax;
+    const int nm = (int)s.dist_n;
+    float t = tmin;
+    for (int it = 0; it < kMaxMarch; it++) {
+        int cx = (int)floorf(u0.x + t * du.x), cy = (int)floorf(u0.y + t * du.y), cz = (int)floorf(u0.z + t * du.z);
+        cx = min(max(cx, 0), nm - 1); cy = min(max(cy, 0), nm - 1); cz = min(max(cz, 0), nm - 1);
+        const unsigned D = __ldg(dist + ((size_t)cz * nm + cy) * nm + cx);
+        if (D < 4u) return false;
+        t += ((float)D - 3.5f) * rd;
+        if (t >= tmax) return true;
+    }
+    return false;
 }
 
 RT_DEV void pushTask(bool want, unsigned id, unsigned* queue, unsigned* count) {
@@ -592,6 +696,7 @@ __global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_const
                 }
                 for (int s = op.set_lo; s < op.set_hi; s++) {
                     float m0 = sr.mint, x0 = sr.maxt;
+                    if (sc.sets[s].wall_ok && shadowClearsWalls(sc.sets[s], sr)) continue;   // a segment inside the room misses its walls
                     anySet1(sc.sets[s], sr);
                     if (sr.mint != m0 || sr.maxt != x0) sr_dirty = true;
                 }
@@ -640,6 +745,14 @@ constexpr int kRefill = RT_REFILL;
 #endif
 #ifndef RT_PIPE_NG
 #define RT_PIPE_NG 0
+#endif
+// RT_CHUNK = k > 0: warps reserve k queue entries per atomic instead of one atomic per refill.  Measured slower (B200, full config,
+// k = 64 / 256: 6573 / 6538 vs 6820 Mrays/s): the refill atomics are not what the walkers wait for, and private chunks cost balance.
+#ifndef RT_CHUNK
+#define RT_CHUNK 0
+#endif
+#if RT_CHUNK
+constexpr int kChunk = RT_CHUNK;
 #endif
 constexpr int kStepBurst = RT_STEP_BURST;   // empty-cell steps per outer iteration
 constexpr int kWalkWarps = 8;               // warps per block
@@ -692,6 +805,10 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
     __shared__ unsigned s_cown[kWalkWarps][kCandCap];
     __shared__ float s_cdiv[kWalkWarps][kCandCap];
     __shared__ unsigned long long s_best[kWalkWarps][32];
+#if RT_CHUNK
+    __shared__ unsigned s_chunk[kWalkWarps][2];   // warp-private piece of the queue: [next, end)
+    if (threadIdx.x < kWalkWarps) { s_chunk[threadIdx.x][0] = 0; s_chunk[threadIdx.x][1] = 0; }
+#endif
     for (unsigned i = threadIdx.x; i < 8192; i += blockDim.x) s_macro[i] = set.macro_occ[i];
     __syncthreads();
     const unsigned mshift = set.macro_shift, mn = set.macro_n;
@@ -803,13 +920,34 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
             if (fin) { writeBack(); fin = false; }
         }
         if (!drained && (__popc(idle) >= kRefill || idle == FULL)) {
+#if RT_CHUNK
+            // Entries come from a warp-private chunk of the queue, reserved kChunk at a time: every warp of every block pops from
+            // ONE counter and same-address atomics retire at about one per nanosecond, so one atomic per refill (~10 entries)
+            // costs a 100 M-entry launch ~10 ms of serialised atomic time and each refill a queueing delay.  The chunk bounds
+            // live in shared memory (they are touched at refills only).  A refill hands out what the chunk still holds; lanes left
+            // without an entry are served by the next iteration from a fresh chunk.
+            if (s_chunk[wid][0] == s_chunk[wid][1]) {
+                unsigned nb = 0;
+                if (lane == 0) nb = atomicAdd(head, (unsigned)kChunk);
+                nb = __shfl_sync(FULL, nb, 0);
+                if (lane == 0) { s_chunk[wid][0] = min(nb, count); s_chunk[wid][1] = min(nb + (unsigned)kChunk, count); }
+                __syncwarp();
+            }
+            const unsigned cpos = s_chunk[wid][0], cend = s_chunk[wid][1];
+            const unsigned base = cpos;
+            const unsigned limit = cend;
+            __syncwarp();
+            if (lane == 0) s_chunk[wid][0] = min(cpos + (unsigned)__popc(idle), cend);
+#else
             unsigned base = 0;
             int leader = __ffs(idle) - 1;
             if ((int)lane == leader) base = atomicAdd(head, (unsigned)__popc(idle));
             base = __shfl_sync(FULL, base, leader);
+            const unsigned limit = count;
+#endif
             if (!have) {
                 unsigned idx = base + __popc(idle & lt);
-                if (idx < count) {
+                if (idx < limit) {
                     slot = ldS(w.queue + idx);
                     const float4* src = (ANY ? w.sh : w.ray) + rayBase(slot);
                     float4 r0 = ldS(src), r1 = ldS(src + n);
@@ -827,7 +965,12 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
                     have = true;
                 }
             }
+#if RT_CHUNK
+            __syncwarp();
+            if (cend >= count && base + __popc(idle) >= cend) drained = true;   // the queue's last chunk, used up
+#else
             if (base + __popc(idle) >= count) drained = true;
+#endif
             idle = __ballot_sync(FULL, !have);
         }
         if (idle == FULL) break;
@@ -985,6 +1128,65 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
     }
 }
 
+// Queue filter: drops the entries whose walk is provably empty (walkProvablyEmpty) or cannot produce an accepted hit at all
+// (the box is entered beyond the stored maxt: every cell interval starts at or after tmin, every acceptance needs
+// t < champ_t = maxt; 0.01 % of slack for the rounding of the first cell boundaries) and writes the survivors, warp-compacted, to the
+// queue the walker reads.  Entry order across warps follows the atomics; the walk of a ray does not depend on it.
+// Two kernels.  k_filter_mark decides: one warp per 32 entries, no block-wide synchronisation, so a warp only waits for the
+// slowest march among its own 32 rays and the SM hides the chain of dependent loads behind its other 63 warps; the decisions
+// go out as one 32-bit mask per warp.  k_filter_pack compacts: rounds of 256 entries, warp ballots -> shared prefix -> ONE
+// atomicAdd per block and round (all launches of a stage add to one counter and same-address atomics retire at about one per
+// nanosecond: with one atomic per warp the first version spent 3.7 ms per launch on 3.3 M of them, three times its own work;
+// with the march inside the synchronised rounds it still took 2.7 ms).
+constexpr int kFilterBlocks = 8;   // per SM
+template <bool ANY>
+__global__ void __launch_bounds__(256) k_filter_mark(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w, unsigned* masks,
+                                                     unsigned n, int qslot) {
+    const unsigned count = w.qctr[2 * qslot];
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned words = (count + 31u) / 32u;
+    for (unsigned word = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < words; word += (gridDim.x * blockDim.x) >> 5) {
+        const unsigned idx = word * 32u + lane;
+        bool keep = false;
+        if (idx < count) {
+            const unsigned e = ldS(w.queue + idx);
+            size_t base = e;
+            if (ANY) { const unsigned l = e / n; base = (size_t)(2 * l) * n + (e - l * n); }
+            const float4* src = (ANY ? w.sh : w.ray) + base;
+            const float4 r0 = ldS(src), r1 = ldS(src + n);
+            const f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
+            const AabbHit bi = interAABB(o, d, set.g.bound);
+            keep = !(bi.tmin * 0.9999f > r1.w) && !walkProvablyEmpty(o, d, bi.tmin, bi.tmax, set);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) masks[word] = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_filter_pack(const __grid_constant__ WaveState w, const __grid_constant__ WaveState wf,
+                                                     const unsigned* masks, int qslot) {
+    __shared__ unsigned s_cnt[8];
+    __shared__ unsigned s_base;
+    const unsigned count = w.qctr[2 * qslot];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned rounds = (count + 255u) / 256u;
+    for (unsigned round = blockIdx.x; round < rounds; round += gridDim.x) {
+        const unsigned idx = round * 256u + threadIdx.x;
+        const unsigned m = (round * 8u + wid) * 32u < count ? masks[round * 8u + wid] : 0u;
+        const bool keep = (m >> lane) & 1u;
+        if (lane == 0) s_cnt[wid] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned tot = 0;
+            for (int k = 0; k < 8; k++) { const unsigned c = s_cnt[k]; s_cnt[k] = tot; tot += c; }
+            s_base = tot ? atomicAdd(wf.qctr + 2 * qslot, tot) : 0u;
+        }
+        __syncthreads();
+        if (keep) stS(wf.queue + s_base + s_cnt[wid] + __popc(m & ((1u << lane) - 1u)), ldS(w.queue + idx));
+        __syncthreads();   // s_cnt / s_base are reused by the next round
+    }
+}
+
 // Builds the stage list for a scene (host) and runs one tile through it.
 struct Stage { bool is_walk; StageOp op; int set; bool any; int qslot; };
 
@@ -1091,7 +1293,11 @@ int ensureWaveBuffers(rt_render* r) {
     const size_t nl = r->scene->lights.size() ? r->scene->lights.size() : 1;
     A((void**)&r->w_sh, sizeof(float4) * 2 * n * nl);      // one shadow ray per light and slot
     A((void**)&r->w_queue, sizeof(unsigned) * n * nl);     // any-hit walks queue (light, slot) entries
-    A((void**)&r->w_qctr, sizeof(unsigned) * 2 * kMaxStages);
+    A((void**)&r->w_qctr, sizeof(unsigned) * 4 * kMaxStages);   // {count, head} per walk stage: [0, 2K) as pushed, [2K, 4K) filtered
+    if (skipEmptyWalks()) {
+        A((void**)&r->w_queue_f, sizeof(unsigned) * n * nl);              // what the queue filter leaves for the walker
+        A((void**)&r->w_masks, sizeof(unsigned) * ((n * nl + 31) / 32 + 8));   // its keep decisions, one bit per entry
+    }
     return rc;
 }
 
@@ -1139,8 +1345,12 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
         return RT_OK;
     }
     WaveState w = {r->w_ray, r->w_poi, r->w_atte, r->w_sh, r->w_queue, r->w_qctr};
-    RT_CUDA(ctx, cudaMemsetAsync(r->w_qctr, 0, sizeof(unsigned) * 2 * kMaxStages, ctx->stream));
+    WaveState wf = w;   // the filtered queue (k_filter) the walkers read when the empty-walk proof is on
+    wf.queue = r->w_queue_f;
+    wf.qctr = r->w_qctr + 2 * kMaxStages;
+    RT_CUDA(ctx, cudaMemsetAsync(r->w_qctr, 0, sizeof(unsigned) * 4 * kMaxStages, ctx->stream));
     const unsigned n = a.n_local;
+    const WaveState& w0 = w;
     for (const Stage& s : stages) {
         if (!s.is_walk) {
             // a seed upload still in flight (rt_render_write_local_seeds_async) is waited for here, in front of the
@@ -1153,6 +1363,17 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
         } else {
             const SetDev& set = sc.sets[s.set];
             const int walk_blocks = ctx->prop.multiProcessorCount * kWalkMinBlocks;   // persistent: one resident wave
+            const bool filtered = set.macro_dist != nullptr && r->w_queue_f != nullptr;
+            if (filtered) {
+                RT_TRY_W(rt_time_mark(r, 0));   // charged to the stage class: it is queue preparation
+                const int fb = ctx->prop.multiProcessorCount * kFilterBlocks;
+                if (s.any) k_filter_mark<true><<<fb, 256, 0, ctx->stream>>>(set, w, r->w_masks, n, s.qslot);
+                else k_filter_mark<false><<<fb, 256, 0, ctx->stream>>>(set, w, r->w_masks, n, s.qslot);
+                RT_LAUNCH_CHECK(ctx, "wave_filter_mark");
+                k_filter_pack<<<fb, 256, 0, ctx->stream>>>(w, wf, r->w_masks, s.qslot);
+                RT_LAUNCH_CHECK(ctx, "wave_filter_pack");
+            }
+            const WaveState& w = filtered ? wf : *&w0;
             RT_TRY_W(rt_time_mark(r, (set.kind == PRIM_SPHERE ? 1 : 3) + (s.any ? 1 : 0)));
             if (set.kind == PRIM_SPHERE) {
                 if (s.any) k_walk_pairs<PRIM_SPHERE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
@@ -1168,6 +1389,41 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
 }
 
 }  // namespace
+
+namespace {
+__global__ void k_skipProbe(const __grid_constant__ SetDev set, const Ray* rays, unsigned n, unsigned char* out) {
+    unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    RayR ray = loadRay(rays + id);
+    unsigned char flag = 0;
+    if (ray.mint != ray.maxt) {
+        if (set.g.n > 1) {
+            const AabbHit bi = interAABB(ray.o, ray.d, set.g.bound);
+            if (bi.v && walkProvablyEmpty(ray.o, ray.d, bi.tmin, bi.tmax, set)) flag = 1;
+        } else if (set.wall_ok && shadowClearsWalls(set, ray)) {
+            flag = 1;
+        }
+    }
+    out[id] = flag;
+}
+}  // namespace
+
+// Diagnostic: which rays of a Ray buffer would the wavefront path NOT send to the queue walker of geometry set `set_index`
+// because their walk provably crosses empty cells only (walkProvablyEmpty)?  out_flags: one byte per ray.
+extern "C" int rt_scene_probe_empty_walks(rt_scene* s, unsigned set_index, const void* rays, unsigned n, void* out_flags_u8) {
+    if (!s || !rays || !out_flags_u8 || set_index >= s->sets.size()) return RT_ERR_INVALID;
+    rt_ctx* ctx = s->ctx;
+    if (!n) return RT_OK;
+    rt_render tmp;
+    tmp.ctx = ctx;
+    tmp.scene = s;
+    SceneDev sc;
+    int rc = buildSceneDev(&tmp, sc);
+    if (rc) return rc;
+    k_skipProbe<<<rt_blocks(n, 256), 256, 0, ctx->stream>>>(sc.sets[set_index], (const Ray*)rays, n, (unsigned char*)out_flags_u8);
+    RT_LAUNCH_CHECK(ctx, "skipProbe");
+    return RT_OK;
+}
 
 int rt_fused_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, const float2* rpp1_coords) {
     rt_ctx* ctx = r->ctx;

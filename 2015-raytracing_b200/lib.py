@@ -141,6 +141,7 @@ _SIGS = {
     "rt_scene_set_materials": ([P, P, U], I),
     "rt_scene_add_set": ([P, C.POINTER(Grid), P, I, U], I),
     "rt_scene_add_light": ([P, P, P, P], I),
+    "rt_scene_probe_empty_walks": ([P, U, P, U, P], I),
     "rt_render_create": ([P, P, C.POINTER(RenderOpts), PP], I),
     "rt_render_destroy": ([P], I),
     "rt_render_set_seeds": ([P, P, Z, I], I),

@@ -267,6 +267,14 @@ int rt_scene_add_set(rt_scene*, const rt_grid* grid, const float bound[8], int i
 /* Light.toShadowInfo / toSceneRenderInfo / toLightRenderInfo, A10/code.js:323-352 */
 int rt_scene_add_light(rt_scene*, const float shadow_info[16], const float scene_info[16], const float light_info[16]);
 
+/* Diagnostic of the wavefront path (ours): which rays of a Ray buffer (48-byte records) would NOT be sent to the queue
+ * walker of geometry set `set_index` because their whole walk through that set's grid provably crosses empty cells only and is
+ * skipped (a third of the walks of BASELINE config 5); for a 1-cell set of wall triangles: which shadow segments (unit direction,
+ * maxt = length) are not tested against it because both ends lie inside the room.  out_flags: one byte per ray on the device, 1 = skipped.  The parity tests
+ * check every flagged ray against the instrumented reference kernels (it must visit no reference there).  RT2015_NO_SKIP=1 in the
+ * environment switches the skip off. */
+int rt_scene_probe_empty_walks(rt_scene*, unsigned set_index, const void* rays, unsigned n, void* out_flags_u8);
+
 typedef struct {
     unsigned cols, rows;          /* canvas size */
     unsigned rays_per_pixel;      /* slots per pixel; > 1 must be a perfect square (stratified lens grid) */

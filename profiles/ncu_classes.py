@@ -44,7 +44,7 @@ def classify(kernel):
         prim = "sphere" if m.group(1) == "0" else "triangle"
         anyh = m.group(2) in ("1", "true")
         return "walk_%s_%s" % (prim, "any" if anyh else "closest")
-    if "k_stage<" in k:
+    if "k_stage<" in k or "k_filter" in k:   # the queue filter is charged to the stage class by bench.py's timing too
         return "stage"
     if "f_sumSlots" in k or "f_accumToPixel" in k:
         return "sum_copy"

@@ -281,3 +281,145 @@ def test_a09_at_default_100_rays_per_pixel(rt, gpu_ctx, ref_lib, tmp_path, name)
     acu_f, pix_f, matid_f, _ = rt.assignments.a089_render_fused(gpu_ctx, p_scene, cols, rows, 9, rpp, n_slabs)
     assert np.array_equal(acu_f.view(np.uint32), acu.view(np.uint32)) and np.array_equal(matid_f, matid) and np.array_equal(pix_f, pix)
     assert P["assignment"] == 9
+
+
+def _probe_rays(rng, bmin, bmax, n):
+    """Random and adversarial rays around a set's box (o, d float32; not normalised on purpose for some)."""
+    c, ext = (bmin + bmax) / 2, (bmax - bmin)
+    o = np.empty((n, 3), np.float64)
+    d = np.empty((n, 3), np.float64)
+    k = n // 8
+    # (a) from a shell around the box towards random points in / near it
+    u = rng.normal(size=(3 * k, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    o[:3 * k] = c + u * ext.max() * rng.uniform(0.9, 3.0, size=(3 * k, 1))
+    d[:3 * k] = (c + rng.uniform(-0.8, 0.8, size=(3 * k, 3)) * ext) - o[:3 * k]
+    # (b) origins inside the box, random directions
+    o[3 * k:5 * k] = bmin + rng.uniform(0, 1, size=(2 * k, 3)) * ext
+    d[3 * k:5 * k] = rng.normal(size=(2 * k, 3))
+    # (c) far origins (large entry parameters: the reference's t_next sequences drift)
+    u = rng.normal(size=(k, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    o[5 * k:6 * k] = c + u * ext.max() * rng.choice([30.0, 1e3, 1e5], size=(k, 1))
+    d[5 * k:6 * k] = (c + rng.uniform(-0.7, 0.7, size=(k, 3)) * ext) - o[5 * k:6 * k]
+    # (d) axis-parallel and nearly axis-parallel directions (zero / tiny components)
+    o[6 * k:7 * k] = c + rng.uniform(-1.5, 1.5, size=(k, 3)) * ext
+    dd = rng.normal(size=(k, 3))
+    dd[np.arange(k), rng.integers(0, 3, k)] *= rng.choice([0.0, 1e-30, 1e-12, 1e-6], size=k)
+    d[6 * k:7 * k] = dd
+    # (e) grazing: along the box faces and the surface-hugging corners
+    face = rng.integers(0, 3, n - 7 * k)
+    oo = bmin + rng.uniform(0, 1, size=(n - 7 * k, 3)) * ext
+    oo[np.arange(len(face)), face] = np.where(rng.random(len(face)) < 0.5, bmin[face], bmax[face]) + rng.choice([0.0, 1e-6, -1e-6, 1e-3], size=len(face)) * ext[face]
+    oo -= 2.0 * ext * rng.normal(size=(len(face), 1)) * 0  # stay on the face
+    dg = rng.normal(size=(len(face), 3))
+    dg[np.arange(len(face)), face] *= rng.choice([0.0, 1e-9, 1e-4, 0.05], size=len(face))
+    o[7 * k:] = oo - dg * rng.uniform(0.0, 2.0, size=(len(face), 1))
+    d[7 * k:] = dg
+    nrm = np.linalg.norm(d, axis=1, keepdims=True)
+    unit = rng.random(n) < 0.8
+    d[unit] = d[unit] / np.where(nrm[unit] > 0, nrm[unit], 1.0)
+    rays = np.zeros(n, OR.RAY)
+    rays["o"][:, :3] = o.astype(np.float32)
+    rays["d"][:, :3] = d.astype(np.float32)
+    rays["mint"] = 0.0
+    rays["maxt"] = np.inf
+    return rays
+
+
+@pytest.mark.parametrize("mesh_uv,nslabs", [((200, 100), 64), ((160, 80), 128), ((40, 20), 10)])
+def test_skipped_walks_cross_empty_cells_only(rt, instr_lib, tmp_path, mesh_uv, nslabs):
+    """The wavefront path does not queue a ray whose walk it can PROVE crosses empty cells only (walkProvablyEmpty, a march through
+    a distance field of the coarse occupancy).  The proof must be conservative: every ray it flags must, in the reference's own
+    kernel (instrumented build), visit cells but test NO reference -- on random rays, far origins (drifting t_next sequences),
+    axis-parallel directions and rays grazing the box faces.  It must also be worth having: a fair share of the zero-test walks
+    is flagged."""
+    o_scene, p_scene = util.make_scene_pair(tmp_path, 64, 48, mesh_uv=mesh_uv, mesh_nslabs=nslabs)
+    om = o_scene["meshes"][0]
+    prep = OR.prepare_a10(o_scene, 1)
+    mesh = prep["sets"][-1]
+    bmin, bmax = np.array(om.bounds.min, np.float64), np.array(om.bounds.max, np.float64)
+    n = 1 << 21
+    rays = _probe_rays(np.random.Generator(np.random.PCG64(4242 + nslabs)), bmin, bmax, n)
+    # the reference: meshTrace (closest hit) over the same rays with the counting hooks
+    hit, cells, tests = np.zeros(n, np.uint32), np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+    instr_lib.set_stats(hit, cells, tests)
+    try:
+        pois = np.zeros(n, OR.POI10)
+        ro = rays.copy()
+        instr_lib.a10_meshTrace(n, pois, ro, mesh["pos"], mesh["normal"], mesh["box"], mesh["matid"], mesh["aabb"], mesh["n"])
+    finally:
+        instr_lib.set_stats(None, None, None)
+    r = rt.Renderer(p_scene, 64, 48, 4)
+    r.preRender(OR.make_seeds(64 * 48 * 4, 1))
+    try:
+        ctx = r.ctx
+        d_rays, d_flags = ctx.upload(rays), ctx.alloc(n)
+        ctx.check(rt.lib.dll.rt_scene_probe_empty_walks(r.h_scene, len(prep["sets"]) - 1, d_rays, n, d_flags))
+        flags = ctx.download(d_flags, np.uint8, n).astype(bool)
+        ctx.free(d_rays)
+        ctx.free(d_flags)
+    finally:
+        r.postRender()
+    walked = cells > 0
+    assert not (flags & ~walked).any(), "a ray that never enters the grid was flagged"
+    bad = flags & (tests > 0)
+    assert not bad.any(), "%d flagged rays test references in the reference kernel (first: %d, %d tests)" % (bad.sum(), np.flatnonzero(bad)[0], tests[bad][0])
+    assert not (flags & (hit != NONE)).any()
+    empty = walked & (tests == 0)
+    share = flags.sum() / max(int(empty.sum()), 1)
+    assert empty.sum() > 1000
+    if nslabs >= 64:
+        assert share > 0.3, "only %.1f %% of the zero-test walks are proven empty" % (100 * share)
+
+
+def test_shadow_rays_skipped_against_walls_are_unblocked(rt, ref_lib, tmp_path):
+    """The stage kernels do not test a shadow segment against a room's wall triangles when both its ends lie inside the room
+    with rounding-proof margins (shadowClearsWalls).  Every segment the predicate flags must be left unblocked by the
+    reference's own triangleShadowTrace -- on segments hugging the walls, ending at / beyond them, and nearly parallel to them."""
+    o_scene, p_scene = util.make_scene_pair(tmp_path, 64, 48, mesh_uv=(24, 12), mesh_nslabs=8)
+    prep = OR.prepare_a10(o_scene, 1)
+    kinds = [q["kind"] for q in prep["sets"]]
+    k = kinds.index("triangle")
+    tri = prep["sets"][k]
+    rng = np.random.Generator(np.random.PCG64(99))
+    n = 1 << 21
+    lo, hi = np.array([-0.98, -0.98, -0.98]), np.array([0.98, 0.98, 2.5])   # the synthetic room (tests/synth.py)
+    o = lo + rng.uniform(0, 1, size=(n, 3)) * (hi - lo)
+    # a third of the origins sit on a wall, pushed in by the renderer's 0.001 (or less, or outside)
+    m = n // 3
+    ax = rng.integers(0, 3, m)
+    side = rng.random(m) < 0.5
+    off = rng.choice([1e-3, 1e-3, 1e-4, 1e-5, 0.0, -1e-3], size=m)
+    o[np.arange(m), ax] = np.where(side, lo[ax] + off, hi[ax] - off)
+    q = lo + rng.uniform(-0.05, 1.05, size=(n, 3)) * (hi - lo)          # end points: inside, near the walls, some outside
+    par = rng.random(n) < 0.2                                             # nearly parallel to a wall
+    ax2 = rng.integers(0, 3, n)
+    q[par, ax2[par]] = o[par, ax2[par]] + rng.choice([0.0, 1e-7, 1e-5, 1e-3], size=par.sum()) * rng.choice([-1, 1], size=par.sum())
+    d = q - o
+    L = np.linalg.norm(d, axis=1)
+    keep = L > 1e-6
+    o, d, L = o[keep], d[keep] / L[keep, None], L[keep]
+    n = len(o)
+    rays = np.zeros(n, OR.RAY)
+    rays["o"][:, :3] = o.astype(np.float32)
+    rays["d"][:, :3] = d.astype(np.float32)
+    rays["d"][:, :3] /= np.linalg.norm(rays["d"][:, :3].astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    rays["mint"] = 0.0
+    rays["maxt"] = L.astype(np.float32)
+    after = rays.copy()
+    ref_lib.a10_triangleShadowTrace(n, after, tri["pos"], tri["box"], tri["aabb"], tri["n"])
+    blocked = after["mint"] == after["maxt"]
+    r = rt.Renderer(p_scene, 64, 48, 4)
+    r.preRender(OR.make_seeds(64 * 48 * 4, 1))
+    try:
+        ctx = r.ctx
+        d_rays, d_flags = ctx.upload(rays), ctx.alloc(n)
+        ctx.check(rt.lib.dll.rt_scene_probe_empty_walks(r.h_scene, k, d_rays, n, d_flags))
+        flags = ctx.download(d_flags, np.uint8, n).astype(bool)
+        ctx.free(d_rays)
+        ctx.free(d_flags)
+    finally:
+        r.postRender()
+    assert blocked.sum() > 1000 and (~blocked).sum() > 1000
+    bad = flags & blocked
+    assert not bad.any(), "%d flagged segments are blocked by a wall in the reference kernel (first: %d)" % (bad.sum(), np.flatnonzero(bad)[0])
+    assert flags.mean() > 0.2, "only %.1f %% of the segments are skipped" % (100 * flags.mean())
