@@ -34,6 +34,7 @@ struct SetDev {
     const unsigned char* macro_dist;   // heavy sets: chessboard distance of every cell of the distance field to the nearest occupied one (or null)
     float dist_inv[3];         // world -> field-index scale per axis
     unsigned dist_shift, dist_n;       // field cells are (2^dist_shift)^3 grid cells, dist_n per axis
+    unsigned n_refs;
     int wall_ok;               // 1-cell triangle sets made of axis-aligned planar triangles ("walls"): see shadowClearsWalls
     float wall_lo[3], wall_hi[3], wall_scale;
 };
@@ -139,8 +140,25 @@ RT_DEV void flushProfile(unsigned* prof, unsigned long long* table, int set, int
 
 // The same two functions for the per-slot stage kernels, where every inline set is a ONE-cell grid (multi-cell
 // sets are "heavy" and go to the queue walkers): only singleCellWalk is compiled in.
+// A small sphere set is cheaper to rule out by its spheres than by its box: interSphere's first rejection is dis < 0
+// (A10/code.cl:199-215), computed from the ray alone with the same operations here; when it fires for every sphere of the set the
+// reference finds nothing whether or not the ray hits the set's box, so the six IEEE divisions of the slab test are skipped.
+RT_DEV bool missesAllSpheres(const SetDev& s, f3 o, f3 d) {
+    if (s.kind != PRIM_SPHERE || s.n_refs == 0 || s.n_refs > 2) return false;
+    const float a = dot(d, d);
+    for (unsigned i = 0; i < s.n_refs; i++) {
+        const float4 sp = __ldg(s.g.prim + i);
+        const f3 omc = o - mk3(sp.x, sp.y, sp.z);
+        const float b = 2.0f * dot(omc, d);
+        const float c = dot(omc, omc) - sp.w;
+        if (!(fmaf(-4.0f * c, a, b * b) < 0.0f)) return false;
+    }
+    return true;
+}
+
 RT_DEV void closestSet1(const SetDev& s, RayR& ray, PoiR& poi) {
     if (ray.mint == ray.maxt) return;
+    if (missesAllSpheres(s, ray.o, ray.d)) return;
     AabbFar binter = interAABBFar(ray.o, ray.d, s.g.bound);
     if (!binter.v) return;
     Hit h;
@@ -161,6 +179,7 @@ RT_DEV void closestSet1(const SetDev& s, RayR& ray, PoiR& poi) {
 }
 RT_DEV void anySet1(const SetDev& s, RayR& sr) {
     if (sr.mint == sr.maxt) return;
+    if (missesAllSpheres(s, sr.o, sr.d)) return;
     AabbFar binter = interAABBFar(sr.o, sr.d, s.g.bound);
     if (!binter.v) return;
     Hit h;
@@ -358,6 +377,7 @@ int buildSceneDev(rt_render* r, SceneDev& sc) {
         for (int a = 0; a < 3; a++) d.dist_inv[a] = in.dist_inv[a];
         d.dist_shift = in.dist_shift;
         d.dist_n = in.dist_n;
+        d.n_refs = in.grid.n_refs;
         d.wall_ok = (in.wall_ok && skipWallTests()) ? 1 : 0;
         for (int a = 0; a < 3; a++) { d.wall_lo[a] = in.wall_lo[a]; d.wall_hi[a] = in.wall_hi[a]; }
         d.wall_scale = in.wall_scale;
@@ -740,20 +760,6 @@ constexpr int kRefill = RT_REFILL;
 #ifndef RT_SKIP2
 #define RT_SKIP2 0
 #endif
-#ifndef RT_OPAQUE_TID
-#define RT_OPAQUE_TID 0
-#endif
-#ifndef RT_PIPE_NG
-#define RT_PIPE_NG 0
-#endif
-// RT_CHUNK = k > 0: warps reserve k queue entries per atomic instead of one atomic per refill.  Measured slower (B200, full config,
-// k = 64 / 256: 6573 / 6538 vs 6820 Mrays/s): the refill atomics are not what the walkers wait for, and private chunks cost balance.
-#ifndef RT_CHUNK
-#define RT_CHUNK 0
-#endif
-#if RT_CHUNK
-constexpr int kChunk = RT_CHUNK;
-#endif
 constexpr int kStepBurst = RT_STEP_BURST;   // empty-cell steps per outer iteration
 constexpr int kWalkWarps = 8;               // warps per block
 constexpr int kWalkMinBlocks = RT_WALK_MINB; // resident blocks per SM the register budget is tuned for
@@ -805,20 +811,10 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
     __shared__ unsigned s_cown[kWalkWarps][kCandCap];
     __shared__ float s_cdiv[kWalkWarps][kCandCap];
     __shared__ unsigned long long s_best[kWalkWarps][32];
-#if RT_CHUNK
-    __shared__ unsigned s_chunk[kWalkWarps][2];   // warp-private piece of the queue: [next, end)
-    if (threadIdx.x < kWalkWarps) { s_chunk[threadIdx.x][0] = 0; s_chunk[threadIdx.x][1] = 0; }
-#endif
     for (unsigned i = threadIdx.x; i < 8192; i += blockDim.x) s_macro[i] = set.macro_occ[i];
     __syncthreads();
     const unsigned mshift = set.macro_shift, mn = set.macro_n;
-    unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#if RT_OPAQUE_TID
-    // ptxas otherwise REMATERIALISES lane / warp id from SR_TID.X (a slow S2R) all over the hot loop instead of keeping
-    // two registers: ncu charged 5.7 % of the kernel's warp instructions to the line that first reads threadIdx
-    asm volatile("" : "+r"(lane));
-    asm volatile("" : "+r"(wid));
-#endif
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const unsigned FULL = 0xffffffffu;
     const unsigned long long NONE = ~0ull;
@@ -920,31 +916,11 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
             if (fin) { writeBack(); fin = false; }
         }
         if (!drained && (__popc(idle) >= kRefill || idle == FULL)) {
-#if RT_CHUNK
-            // Entries come from a warp-private chunk of the queue, reserved kChunk at a time: every warp of every block pops from
-            // ONE counter and same-address atomics retire at about one per nanosecond, so one atomic per refill (~10 entries)
-            // costs a 100 M-entry launch ~10 ms of serialised atomic time and each refill a queueing delay.  The chunk bounds
-            // live in shared memory (they are touched at refills only).  A refill hands out what the chunk still holds; lanes left
-            // without an entry are served by the next iteration from a fresh chunk.
-            if (s_chunk[wid][0] == s_chunk[wid][1]) {
-                unsigned nb = 0;
-                if (lane == 0) nb = atomicAdd(head, (unsigned)kChunk);
-                nb = __shfl_sync(FULL, nb, 0);
-                if (lane == 0) { s_chunk[wid][0] = min(nb, count); s_chunk[wid][1] = min(nb + (unsigned)kChunk, count); }
-                __syncwarp();
-            }
-            const unsigned cpos = s_chunk[wid][0], cend = s_chunk[wid][1];
-            const unsigned base = cpos;
-            const unsigned limit = cend;
-            __syncwarp();
-            if (lane == 0) s_chunk[wid][0] = min(cpos + (unsigned)__popc(idle), cend);
-#else
             unsigned base = 0;
             int leader = __ffs(idle) - 1;
             if ((int)lane == leader) base = atomicAdd(head, (unsigned)__popc(idle));
             base = __shfl_sync(FULL, base, leader);
             const unsigned limit = count;
-#endif
             if (!have) {
                 unsigned idx = base + __popc(idle & lt);
                 if (idx < limit) {
@@ -965,12 +941,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
                     have = true;
                 }
             }
-#if RT_CHUNK
-            __syncwarp();
-            if (cend >= count && base + __popc(idle) >= cend) drained = true;   // the queue's last chunk, used up
-#else
             if (base + __popc(idle) >= count) drained = true;
-#endif
             idle = __ballot_sync(FULL, !have);
         }
         if (idle == FULL) break;
@@ -1029,43 +1000,15 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
             ref = __shfl_sync(FULL, f.i, own) + (p - s_poff[wid][(rank ? rank : 1u) - 1u]);
             return p < P;
         };
-#if RT_PIPE_NG
-        // software pipeline: the face vector of batch b + 1 is requested BEFORE batch b is culled and tested, so that
-        // its L2 / DRAM latency overlaps that work (ncu: the first use of this load is the kernel's top stall site)
-        unsigned own = 0, ref = 0;
-        bool valid = pairOf(0, own, ref);
-#if RT_PIPE_NG == 1
-        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (PRIM == PRIM_TRIANGLE && valid) q = ldKeep(set.pre_ng + ref);
-#endif
-#endif
         for (unsigned base = 0; base < P; base += 32) {
-#if RT_PIPE_NG
-            unsigned own2 = 0, ref2 = 0;
-            bool valid2 = false;
-#if RT_PIPE_NG == 1
-            float4 q2 = make_float4(0.f, 0.f, 0.f, 0.f);
-#endif
-            if (base + 32 < P) {
-                valid2 = pairOf(base + 32, own2, ref2);
-#if RT_PIPE_NG == 1
-                if (PRIM == PRIM_TRIANGLE && valid2) q2 = ldKeep(set.pre_ng + ref2);   // register double buffer
-#else
-                if (PRIM == PRIM_TRIANGLE && valid2) prefetchLine<1>(set.pre_ng + ref2);   // 2: no registers held, the line waits in the L1
-#endif
-            }
-#else
             unsigned own, ref;
             const bool valid = pairOf(base, own, ref);
-#endif
             bool pass = valid;
             float dv = 0.f;
             if (PRIM == PRIM_TRIANGLE) {
                 const f3 d = mk3(__shfl_sync(FULL, f.w.d.x, own), __shfl_sync(FULL, f.w.d.y, own), __shfl_sync(FULL, f.w.d.z, own));
                 if (valid) {
-#if RT_PIPE_NG != 1
                     float4 q = ldKeep(set.pre_ng + ref);
-#endif
                     dv = dot(mk3(q.x, q.y, q.z), d);
                     pass = dv > 0;   // the reference's first rejection (div <= 0), on the precomputed face vector
                 }
@@ -1095,12 +1038,6 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
                 ncand -= 32;
                 __syncwarp();
             }
-#if RT_PIPE_NG
-            own = own2; ref = ref2; valid = valid2;
-#if RT_PIPE_NG == 1
-            q = q2;
-#endif
-#endif
         }
         if (ncand) testCandidates(ncand);
         __syncwarp();
