@@ -294,14 +294,14 @@ def roofline_of(r, scene, tclass, kern_ms, args, peak, measured_peak, world, clo
            "ncu_profile": ncu[0] if ncu else None, "ncu_profile_note": ncu_why,
            "kernels": per, "step": step, "work_per_set": alg["per_set"][:len(kinds)]}
     if ncu and "stage" in ncu[1]["classes"] and tclass.get("stage", {}).get("launches"):
+        # the stage class = the per-slot stage kernels + the two kernels of the queue filter (one timing mark per filter pair)
         c, v = ncu[1]["classes"]["stage"], tclass["stage"]
-        if c["launches"] == v["launches"] // args.steps:
-            t = v["ms"] / args.steps * 1e-3
-            out["stage"] = {"launches_per_step": c["launches"], "ms_per_step": round(v["ms"] / args.steps, 3),
-                            "traffic_per_step": int(c["dram_read"] + c["dram_write"]),
-                            "frac_dram": round((c["dram_read"] + c["dram_write"]) / t / 1e9 / peak, 4),
-                            "issue_frac": round(c["warp_inst"] / (sms * 4 * clock_hz * t), 4),
-                            "lanes_per_inst": round(c["thread_inst"] / max(c["warp_inst"], 1), 2)}
+        t = v["ms"] / args.steps * 1e-3
+        out["stage"] = {"kernels_per_step": c["launches"], "ms_per_step": round(v["ms"] / args.steps, 3),
+                        "traffic_per_step": int(c["dram_read"] + c["dram_write"]),
+                        "frac_dram": round((c["dram_read"] + c["dram_write"]) / t / 1e9 / peak, 4),
+                        "issue_frac": round(c["warp_inst"] / (sms * 4 * clock_hz * t), 4),
+                        "lanes_per_inst": round(c["thread_inst"] / max(c["warp_inst"], 1), 2)}
     return out
 
 

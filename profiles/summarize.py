@@ -59,12 +59,13 @@ def launches():
     ctot = sum(cls.values())
     with open(os.path.join(OUT, P + "_launches_summary.md"), "w") as f:
         f.write("# %s -- ncu launch list of the bench command\n\n" % P)
-        f.write("Command (B200, 1 GPU): `ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file %s_launches.csv "
-                "python bench.py --steps 1 --warmup 1 --no-cpu-baseline`\n(scene build + warm-up pass + timed pass + the passes of the e2e/profile legs, "
-                "full config: 1920x1080, 256 slots/px, 1 M-triangle mesh, nslabs 128; %d launches captured).\n"
-                "Per-launch times under ncu are serialised and cold-cache; what must agree with bench.py's CUDA-event timing is each kernel's "
-                "SHARE of the step.\n\n" % (P, len(rows)))
-        step = lambda k: k.startswith(("k_stage", "k_walk", "f_sumSlots"))   # the kernels of a pass (k_pathMega<1> = the instrumented work-profile pass)
+        cmd = ("python bench.py --steps 1 --warmup 1 --no-cpu-baseline`\n(scene build + warm-up pass + timed pass + the passes of the e2e/profile legs, " if P.startswith("r1")
+               else "python bench.py --profile-passes 2`\n(scene build + two passes, ")
+        f.write(("Command (B200, 1 GPU): `ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file %s_launches.csv " + cmd +
+                 "full config: 1920x1080, 256 slots/px, 1 M-triangle mesh, nslabs 128; %d launches captured).\n"
+                 "Per-launch times under ncu are serialised and cold-cache; what must agree with bench.py's CUDA-event timing is each kernel's "
+                 "SHARE of the step.\n\n") % (P, len(rows)))
+        step = lambda k: k.startswith(("k_stage", "k_walk", "k_filter", "f_sumSlots"))   # the kernels of a pass (k_pathMega<1> = the instrumented work-profile pass)
         stot = sum(a[1] for k, a in agg.items() if step(k))
         f.write("| kernel | launches | total ms | avg ms | min ms | max ms | share of all | share of the pass kernels |\n|---|---|---|---|---|---|---|---|\n")
         for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
@@ -83,9 +84,14 @@ def full(tag, title, kernel_filter):
     hdr, units = rows[0], rows[1]
     out = io.StringIO()
     out.write("# %s -- `ncu --set full` of %s\n\n" % (P, title))
-    out.write("Command (B200, 1 GPU): `ncu --set full --clock-control none --import-source on --kernel-name regex:%s --launch-skip 24 "
-              "--launch-count 4 -o %s_%s_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (full config; the frame is two tiles, 412 721 664 + 118 119 936 "
-              "slots, a launch serves one tile; the captured launches belong to the small tile).\n\n" % (kernel_filter, P, tag))
+    if P.startswith("r1"):
+        out.write("Command (B200, 1 GPU): `ncu --set full --clock-control none --import-source on --kernel-name regex:%s --launch-skip 24 "
+                  "--launch-count 4 -o %s_%s_full python bench.py --steps 1 --warmup 1 --no-cpu-baseline` (full config; the frame is two tiles, 412 721 664 + 118 119 936 "
+                  "slots, a launch serves one tile; the captured launches belong to the small tile).\n\n" % (kernel_filter, P, tag))
+    else:
+        out.write("Command (B200, 1 GPU): `ncu --set full --clock-control none --import-source on --kernel-name regex:\"%s\" --launch-skip ... "
+                  "--launch-count ... -o %s_%s_full python bench.py --profile-passes 2` (scratch/gpu_prof2.sh; full config, two passes; the frame is two "
+                  "wavefront tiles and a launch serves one tile; the window falls into the second pass).\n\n" % (kernel_filter, P, tag))
     n = len(rows) - 2
     i_n = hdr.index('Kernel Name')
     out.write("| metric | unit | " + " | ".join(short(r[i_n]) for r in rows[2:]) + " |\n|---|---|" + "---|" * n + "\n")
@@ -144,4 +150,5 @@ if __name__ == "__main__":
     bench_lines()
     launches()
     print(full("walk", "the dominant kernel (pair-list queue walker over the 1 M-triangle mesh grid)", "k_walk_pairs"))
-    print(full("stage", "the per-slot stage kernel (ray generation, 1-cell sets, shading, queue push)", "k_stage"))
+    print(full("stage", "the per-slot stage kernels (ray generation, 1-cell sets, shading, queue push) and the queue filter",
+               "k_stage" if P.startswith("r1") else "k_stage|k_filter"))
