@@ -362,6 +362,8 @@ RT_DEV bool interTrianglePre(f3 o, f3 d, float mint, float maxt, float div, f3 p
 // Checked against interTriangle<true> on subnormal numerators and huge divisors in tests/tri_fast_check.cu.
 constexpr float kFastDivMax = 4194304.0f;          // 2^22
 constexpr float kFastNumMin = 1.17549435e-38f;     // FLT_MIN = 2^-126
+// INCL = true: the inclusive range test of A08-A10; false: the exclusive one of A04-A07 (quirk Q9).
+template <bool INCL = true>
 RT_DEV bool interTriangleFast(f3 o, f3 d, float mint, float maxt, float div, f3 p0, f3 e1, f3 e2, float& beta_o, float& gamma_o, float& t_out) {
     if (div <= 0) return false;
     f3 s = o - p0;
@@ -374,7 +376,7 @@ RT_DEV bool interTriangleFast(f3 o, f3 d, float mint, float maxt, float div, f3 
     float gamma = ngm * idiv;
     if (gamma < 0.0f || (gamma + beta) < 0.0f || (gamma + beta) > 1.0f) return false;
     float t = dot(cross(s, e2), e1) * -idiv;
-    if (!(t >= mint && t <= maxt)) return false;
+    if (!(INCL ? (t >= mint && t <= maxt) : (t > mint && t < maxt))) return false;
     beta_o = beta;
     gamma_o = gamma;
     t_out = t;

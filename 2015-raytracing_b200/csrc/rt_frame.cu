@@ -231,6 +231,30 @@ int rt_time_mark(rt_render* r, int cls) {
     return RT_OK;
 }
 
+// Face vectors / edge form (triangle grids) and the coarse occupancy of a registered multi-cell grid, for the queue-walker route of
+// the Assignment-7 launchers: built once, on first use, released with the grid.
+int rt_grid_aux_build(rt_ctx* ctx, rt_ctx::GridAux& g) {
+    if (g.aux_ready) return RT_OK;
+    if (!g.occupancy || g.n_slabs < 2 || g.dims != 3) return RT_ERR_INVALID;
+    unsigned sh = 0;
+    while (((g.n_slabs + (1u << sh) - 1) >> sh) > 64) sh++;
+    g.macro_shift = sh;
+    g.macro_n = (g.n_slabs + (1u << sh) - 1) >> sh;
+    const size_t mcells = (size_t)g.macro_n * g.macro_n * g.macro_n;
+    RT_TRY(rt_buffer_create(ctx, sizeof(unsigned) * 8192, (void**)&g.macro_occ));
+    RT_TRY(rt_buffer_fill(ctx, g.macro_occ, 0, sizeof(unsigned) * 8192));
+    f_macroOccupancy<<<rt_blocks((mcells + 31) / 32 * 32, kBlock), kBlock, 0, ctx->stream>>>(g.occupancy, g.n_slabs, sh, g.macro_n, g.macro_occ);
+    RT_LAUNCH_CHECK(ctx, "macroOccupancy");
+    if (g.kind == 1 && g.n_refs > 0) {
+        RT_TRY(rt_buffer_create(ctx, sizeof(float4) * g.n_refs, (void**)&g.pre_ng));
+        RT_TRY(rt_buffer_create(ctx, sizeof(float4) * 3 * (size_t)g.n_refs, (void**)&g.pre_pe));
+        f_precomputeTriangles<<<rt_blocks(g.n_refs, kBlock), kBlock, 0, ctx->stream>>>((const float4*)g.prim, g.n_refs, g.pre_ng, g.pre_pe);
+        RT_LAUNCH_CHECK(ctx, "precomputeTriangles");
+    }
+    g.aux_ready = true;
+    return RT_OK;
+}
+
 extern "C" {
 
 int rt_scene_create(rt_ctx* ctx, rt_scene** out) {

@@ -411,7 +411,15 @@ int buildGrid(rt_ctx* ctx, int kind, const double* prim_host, const double* nor_
         RT_LAUNCH_CHECK(ctx, "grid_gather");
     }
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->grids.push_back({out->box_size, (const unsigned*)out->occupancy});
+    rt_ctx::GridAux aux;
+    aux.box_size = out->box_size;
+    aux.occupancy = (const unsigned*)out->occupancy;
+    aux.prim = out->prim;
+    aux.n_refs = out->n_refs;
+    aux.n_slabs = out->n_slabs;
+    aux.kind = out->kind;
+    aux.dims = (unsigned)dims;
+    ctx->grids.push_back(aux);
     return RT_OK;
 }
 
@@ -447,7 +455,13 @@ int rt_grid_release(rt_ctx* ctx, rt_grid* g) {
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < ctx->grids.size(); i++)
-        if (ctx->grids[i].first == g->box_size) { ctx->grids.erase(ctx->grids.begin() + i); break; }
+        if (ctx->grids[i].box_size == g->box_size) {
+            cudaFree(ctx->grids[i].pre_ng);
+            cudaFree(ctx->grids[i].pre_pe);
+            cudaFree(ctx->grids[i].macro_occ);
+            ctx->grids.erase(ctx->grids.begin() + i);
+            break;
+        }
     cudaFree(g->prim);
     cudaFree(g->normal);
     cudaFree(g->matid);

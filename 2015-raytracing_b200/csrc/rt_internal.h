@@ -24,16 +24,32 @@ struct rt_ctx {
     // between calls: the device's default pool releases everything at each synchronisation, which made a per-pass
     // 16 MB cudaMallocAsync cost 27 ms
     cudaMemPool_t pool = nullptr;
-    // cell tables of the grids built through this context -> their occupancy bitmaps (1 bit per non-empty cell).  The
-    // launchers keep the reference kernels' argument lists (which only know the cell table), look the bitmap up here and,
-    // when the table is one of ours, skip the two table loads of every EMPTY cell a ray crosses -- same walk, same floats.
-    std::vector<std::pair<const void*, const unsigned*>> grids;
+    // The grids built through this context, keyed by the cell table the launchers receive.  The launchers keep the reference
+    // kernels' argument lists (which only know the cell table); for a table of ours they find the occupancy bits here (skip the
+    // two table loads of every EMPTY cell a ray crosses -- same walk, same floats) and, for the Assignment-7 traces, what the
+    // queue walker needs (face vectors / edge form, coarse occupancy), built on first use.
+    struct GridAux {
+        const void* box_size = nullptr;
+        const unsigned* occupancy = nullptr;
+        const void* prim = nullptr;
+        unsigned n_refs = 0, n_slabs = 0, kind = 0, dims = 3;
+        float4* pre_ng = nullptr;
+        float4* pre_pe = nullptr;
+        unsigned* macro_occ = nullptr;
+        unsigned macro_shift = 0, macro_n = 0;
+        bool aux_ready = false;
+    };
+    std::vector<GridAux> grids;
 };
 
-static inline const unsigned* rt_occupancy_of(const rt_ctx* ctx, const void* box_size) {
-    for (const auto& g : ctx->grids)
-        if (g.first == box_size) return g.second;
+static inline rt_ctx::GridAux* rt_grid_aux_of(rt_ctx* ctx, const void* box_size) {
+    for (auto& g : ctx->grids)
+        if (g.box_size == box_size) return &g;
     return nullptr;
+}
+static inline const unsigned* rt_occupancy_of(rt_ctx* ctx, const void* box_size) {
+    rt_ctx::GridAux* g = rt_grid_aux_of(ctx, box_size);
+    return g ? g->occupancy : nullptr;
 }
 
 static inline cudaError_t rt_scratch_alloc(rt_ctx* ctx, void** p, size_t bytes) {

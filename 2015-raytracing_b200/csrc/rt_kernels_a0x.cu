@@ -9,6 +9,7 @@
 // of the oracle build (x86: truncate to int32, keep the low byte) so images compare exactly;
 // the float buffers are the authoritative comparison.
 #include "rt_device.cuh"
+#include "rt_frame.h"
 #include "rt_internal.h"
 
 using namespace rt;
@@ -783,6 +784,18 @@ __global__ void __launch_bounds__(kBlock) k_a089_frame(const __grid_constant__ A
 
 #define RT_GRID1(n) rt_blocks((n), kBlock), kBlock, 0, ctx->stream
 
+// The queue-walker route of the Assignment-7 traces (rt_walk_a07) applies to a grid this library built (its cell table is registered
+// with the context, with occupancy bits) that is worth the three launches: >= 32 slabs per axis and >= 64 K references, a frame of
+// >= 64 K pixels, and no statistics sinks (those live in the one-thread-per-ray kernel).  RT2015_A07_WALKER=0 switches it off.
+rt_ctx::GridAux* a07WalkerGrid(rt_ctx* ctx, const void* slab_size, const void* prim, unsigned n_slabs, size_t npix) {
+    static const bool on = !(getenv("RT2015_A07_WALKER") && atoi(getenv("RT2015_A07_WALKER")) == 0);
+    if (!on || ctx->st_hit || ctx->st_cells || ctx->st_tests || ctx->st_totals) return nullptr;
+    rt_ctx::GridAux* g = rt_grid_aux_of(ctx, slab_size);
+    if (!g || g->prim != prim || g->n_slabs != n_slabs || g->dims != 3 || !g->occupancy) return nullptr;
+    if (n_slabs < 32 || n_slabs > 1023 || g->n_refs < 65536 || npix < 65536 || npix > 0x7FFFFFFFull) return nullptr;
+    return g;
+}
+
 template <int PRIM>
 void launchA089Closest(rt_ctx* ctx, unsigned total, void* pois, void* rays, const GridView& g, const void* normals, const void* matid) {
     StatPtrs sp = {ctx->st_hit, ctx->st_cells, ctx->st_tests, ctx->st_totals};
@@ -956,6 +969,11 @@ int rt_a07_molTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, un
     if (!pixels || !fcam || !rays || !s_atoms || !bound || !n_slabs || !slab_size) return RT_ERR_INVALID;
     size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
     if (!n) return RT_OK;
+    if (rt_ctx::GridAux* aux = a07WalkerGrid(ctx, slab_size, s_atoms, n_slabs, n)) {   // big grid of ours: through the queue walker
+        int rc = rt_walk_a07(ctx, *aux, PRIM_SPHERE, pixels, fcam, rays, nullptr, bound, n);
+        if (rc) return rc;
+        return RT_OK;
+    }
     GridView g = mkGrid(s_atoms, slab_size, bound, n_slabs, rt_occupancy_of(ctx, slab_size));
     launchA07<PRIM_SPHERE>(ctx, n, pixels, fcam, rays, g, nullptr);
     RT_LAUNCH_CHECK(ctx, "A07 molTrace");
@@ -969,6 +987,11 @@ int rt_a07_meshTrace(rt_ctx* ctx, void* pixels, const float* fcam, void* rays, u
     if (!pixels || !fcam || !rays || !t_pos || !t_normal || !bound || !n_slabs || !slab_size) return RT_ERR_INVALID;
     size_t n = (size_t)(unsigned)fcam[14] * (unsigned)fcam[15];
     if (!n) return RT_OK;
+    if (rt_ctx::GridAux* aux = a07WalkerGrid(ctx, slab_size, t_pos, n_slabs, n)) {
+        int rc = rt_walk_a07(ctx, *aux, PRIM_TRIANGLE, pixels, fcam, rays, t_normal, bound, n);
+        if (rc) return rc;
+        return RT_OK;
+    }
     GridView g = mkGrid(t_pos, slab_size, bound, n_slabs, rt_occupancy_of(ctx, slab_size));
     launchA07<PRIM_TRIANGLE>(ctx, n, pixels, fcam, rays, g, t_normal);
     RT_LAUNCH_CHECK(ctx, "A07 meshTrace");

@@ -8,6 +8,8 @@ hooks at non-arithmetic places of the unmodified code.cl, oracle/cl2cpp.py) or t
 * BASELINE config 5 at its own sampling (256 slots per pixel = 16 x 16 lens grid) and A09 at its default 100 rays per
   pixel (10 x 10), against the oracle on the same inputs.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -423,3 +425,27 @@ def test_shadow_rays_skipped_against_walls_are_unblocked(rt, ref_lib, tmp_path):
     bad = flags & blocked
     assert not bad.any(), "%d flagged segments are blocked by a wall in the reference kernel (first: %d)" % (bad.sum(), np.flatnonzero(bad)[0])
     assert flags.mean() > 0.2, "only %.1f %% of the segments are skipped" % (100 * flags.mean())
+
+
+@pytest.mark.parametrize("what", ["mesh", "mol"])
+def test_a07_big_grids_through_the_queue_walker(rt, gpu_ctx, ref_lib, what):
+    """Config 3 on big grids: molTrace / meshTrace of a library-built grid with >= 32 slabs and >= 64 K references run through the
+    persistent pair-list walker (prepare -> k_walk_pairs with Assignment 7's exclusive triangle test -> finish) instead of one
+    thread per ray.  Same hits, same hit distances, same debug colours as the reference kernels."""
+    import synth
+    cols, rows = 352, 264
+    if what == "mesh":
+        model = synth.synth_mesh(220, 110, seed=7)
+        o_data, p_data, kw, n = OH.parseMeshJSON(model), rt.parseMeshJSON(model), "meshData", 64
+    else:
+        text = synth.synth_pdb(n_atoms=30000, gap_at=123)
+        o_data, p_data, kw, n = OH.parsePDB(text), rt.parsePDB(text), "molData", 40
+    g = (rt.splitMeshData if what == "mesh" else rt.splitMolData)(gpu_ctx, p_data, n)
+    refs = int(g.n_refs)
+    rt.lib.dll.rt_grid_release(gpu_ctx.h, C.byref(g))
+    assert refs >= 65536, "the grid is too small to take the walker route (%d references)" % refs
+    pix_o, rays_o, _ = OR.a07_render(ref_lib, cols, rows, n, **{kw: o_data})
+    pix, maxt = rt.assignments.a07_compute(gpu_ctx, cols, rows, n, **{kw: p_data})
+    assert np.array_equal(maxt.view(np.uint32), rays_o["maxt"].view(np.uint32)), "hit set / hit distances differ"
+    assert np.array_equal(pix.reshape(-1, 4), np.asarray(pix_o).reshape(-1, 4)), "debug colours (shade x cell parity) differ"
+    assert (pix.reshape(-1, 4)[:, :3].sum(axis=1) > 0).mean() > 0.05
