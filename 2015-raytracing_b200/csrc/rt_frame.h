@@ -104,6 +104,5 @@ int rt_fused_tile(rt_render* r, const float* fcam, size_t slot0, unsigned n, con
 
 // Assignment-7 traces of a grid the library built, through the persistent pair-list queue walker (rt_wavefront.cu): same hits, same
 // floats as the one-thread-per-ray kernel, ~3x faster on big grids.  prim = PRIM_SPHERE / PRIM_TRIANGLE.
-int rt_grid_aux_build(rt_ctx* ctx, rt_ctx::GridAux& g);
 int rt_walk_a07(rt_ctx* ctx, rt_ctx::GridAux& g, int prim, void* pixels, const float* fcam, void* rays, const void* normals, const float* bound,
                 size_t npix);

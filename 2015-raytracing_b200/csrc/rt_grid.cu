@@ -419,6 +419,11 @@ int buildGrid(rt_ctx* ctx, int kind, const double* prim_host, const double* nor_
     aux.n_slabs = out->n_slabs;
     aux.kind = out->kind;
     aux.dims = (unsigned)dims;
+    if (rt_grid_wants_walker(aux)) {   // big grid: what the queue-walker route of molTrace / meshTrace needs, now rather than inside a frame
+        int rc = rt_grid_aux_build(ctx, aux);
+        if (rc) return rc;
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     ctx->grids.push_back(aux);
     return RT_OK;
 }

@@ -52,6 +52,13 @@ static inline const unsigned* rt_occupancy_of(rt_ctx* ctx, const void* box_size)
     return g ? g->occupancy : nullptr;
 }
 
+// rt_frame.cu: face vectors / edge form / coarse occupancy of a registered multi-cell grid (for the queue-walker route of the
+// Assignment-7 launchers); built with the grid when it is big enough to take that route.
+int rt_grid_aux_build(rt_ctx* ctx, rt_ctx::GridAux& g);
+static inline bool rt_grid_wants_walker(const rt_ctx::GridAux& g) {
+    return g.dims == 3 && g.occupancy && g.n_slabs >= 32 && g.n_slabs <= 1023 && g.n_refs >= 65536;
+}
+
 static inline cudaError_t rt_scratch_alloc(rt_ctx* ctx, void** p, size_t bytes) {
     return ctx->pool ? cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
 }

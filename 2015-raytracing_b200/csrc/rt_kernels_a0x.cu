@@ -791,8 +791,8 @@ rt_ctx::GridAux* a07WalkerGrid(rt_ctx* ctx, const void* slab_size, const void* p
     static const bool on = !(getenv("RT2015_A07_WALKER") && atoi(getenv("RT2015_A07_WALKER")) == 0);
     if (!on || ctx->st_hit || ctx->st_cells || ctx->st_tests || ctx->st_totals) return nullptr;
     rt_ctx::GridAux* g = rt_grid_aux_of(ctx, slab_size);
-    if (!g || g->prim != prim || g->n_slabs != n_slabs || g->dims != 3 || !g->occupancy) return nullptr;
-    if (n_slabs < 32 || n_slabs > 1023 || g->n_refs < 65536 || npix < 65536 || npix > 0x7FFFFFFFull) return nullptr;
+    if (!g || g->prim != prim || g->n_slabs != n_slabs || !rt_grid_wants_walker(*g) || !g->aux_ready) return nullptr;
+    if (npix < 65536 || npix > 0x7FFFFFFFull) return nullptr;
     return g;
 }
 
