@@ -1082,6 +1082,107 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
 // nanosecond: with one atomic per warp the first version spent 3.7 ms per launch on 3.3 M of them, three times its own work;
 // with the march inside the synchronised rounds it still took 2.7 ms).
 constexpr int kFilterBlocks = 8;   // per SM
+#ifndef RT_OCT_SORT
+#define RT_OCT_SORT 0
+#endif
+#if RT_OCT_SORT
+// The survivors leave the filter partitioned by the direction class of their ray -- octant (RT_OCT_SORT = 1), or octant and
+// dominant axis (= 2) -- with slot order kept inside a class up to rounds of 1024, so that the 32 rays of a walker warp step the
+// same way through neighbouring cells.  mark writes a code byte per entry (0 = dropped, 1 + class) and the class totals; pack
+// scatters into the classes' segments.
+constexpr int kDirGrid = RT_OCT_SORT >= 4 ? 8 : 4;   // cube-map cells per face and axis
+constexpr int kDirBins = RT_OCT_SORT >= 4 ? 512 : (RT_OCT_SORT == 3 ? 128 : 32);
+typedef unsigned short DirCode;
+RT_DEV unsigned dirClass(f3 d) {
+#if RT_OCT_SORT >= 3
+    // cube-map cells: the face of the dominant component (6) x a 4 x 4 (RT_OCT_SORT = 3) grid of the other two, relative to it
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    float m, u, v;
+    unsigned face;
+    if (ax >= ay && ax >= az) { m = ax; u = d.y; v = d.z; face = d.x < 0.f ? 1u : 0u; }
+    else if (ay >= az) { m = ay; u = d.x; v = d.z; face = d.y < 0.f ? 3u : 2u; }
+    else { m = az; u = d.x; v = d.y; face = d.z < 0.f ? 5u : 4u; }
+    const float h = 0.5f * (float)kDirGrid;
+    const float r = m > 0.f ? h / m : 0.f;   // (-1, 1) -> (0, kDirGrid)
+    const int iu = min(max((int)(u * r + h), 0), kDirGrid - 1), iv = min(max((int)(v * r + h), 0), kDirGrid - 1);
+    return face * (unsigned)(kDirGrid * kDirGrid) + (unsigned)(iu * kDirGrid + iv);
+#endif
+    const unsigned oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
+#if RT_OCT_SORT == 2
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const unsigned dom = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
+    return oct * 3u + dom;
+#else
+    return oct;
+#endif
+}
+template <bool ANY>
+__global__ void __launch_bounds__(256) k_filter_mark(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w, unsigned* masks,
+                                                     unsigned n, int qslot) {
+    __shared__ unsigned s_hist[kDirBins];
+    for (int k = threadIdx.x; k < kDirBins; k += 256) s_hist[k] = 0;
+    __syncthreads();
+    DirCode* codes = (DirCode*)masks;
+    const unsigned count = w.qctr[2 * qslot];
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned words = (count + 31u) / 32u;
+    for (unsigned word = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; word < words; word += (gridDim.x * blockDim.x) >> 5) {
+        const unsigned idx = word * 32u + lane;
+        if (idx < count) {
+            const unsigned e = ldS(w.queue + idx);
+            size_t base = e;
+            if (ANY) { const unsigned l = e / n; base = (size_t)(2 * l) * n + (e - l * n); }
+            const float4* src = (ANY ? w.sh : w.ray) + base;
+            const float4 r0 = ldS(src), r1 = ldS(src + n);
+            const f3 o = mk3(r0.x, r0.y, r0.z), d = mk3(r1.x, r1.y, r1.z);
+            const AabbHit bi = interAABB(o, d, set.g.bound);
+            const bool keep = !(bi.tmin * 0.9999f > r1.w) && !walkProvablyEmpty(o, d, bi.tmin, bi.tmax, set);
+            const unsigned cls = dirClass(d);
+            codes[idx] = keep ? (DirCode)(1u + cls) : (DirCode)0;
+            if (keep) atomicAdd(&s_hist[cls], 1u);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kDirBins; k += 256)
+        if (s_hist[k]) atomicAdd(w.qctr + 4 * kMaxStages + 2 * kDirBins * qslot + k, s_hist[k]);
+}
+
+__global__ void __launch_bounds__(256) k_filter_pack(const __grid_constant__ WaveState w, const __grid_constant__ WaveState wf,
+                                                     const unsigned* masks, int qslot) {
+    __shared__ unsigned s_loc[kDirBins], s_glob[kDirBins], s_base[kDirBins];
+    const DirCode* codes = (const DirCode*)masks;
+    const unsigned count = w.qctr[2 * qslot];
+    const unsigned* tot = w.qctr + 4 * kMaxStages + 2 * kDirBins * qslot;
+    unsigned* pos = w.qctr + 4 * kMaxStages + 2 * kDirBins * qslot + kDirBins;
+    if (threadIdx.x == 0) {
+        unsigned acc = 0;
+        for (int k = 0; k < kDirBins; k++) { s_base[k] = acc; acc += tot[k]; }
+        if (blockIdx.x == 0) wf.qctr[2 * qslot] = acc;   // what the walker will find in the filtered queue
+    }
+    const unsigned rounds = (count + 1023u) / 1024u;
+    for (unsigned round = blockIdx.x; round < rounds; round += gridDim.x) {
+        for (int k = threadIdx.x; k < kDirBins; k += 256) s_loc[k] = 0;
+        __syncthreads();
+        unsigned code[4], rank[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned idx = round * 1024u + k * 256u + threadIdx.x;
+            code[k] = idx < count ? codes[idx] : 0u;
+            rank[k] = code[k] ? atomicAdd(&s_loc[code[k] - 1u], 1u) : 0u;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < kDirBins; k += 256) s_glob[k] = s_loc[k] ? atomicAdd(pos + k, s_loc[k]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (code[k]) {
+                const unsigned o = code[k] - 1u;
+                stS(wf.queue + s_base[o] + s_glob[o] + rank[k], ldS(w.queue + round * 1024u + k * 256u + threadIdx.x));
+            }
+        __syncthreads();
+    }
+}
+#else
 template <bool ANY>
 __global__ void __launch_bounds__(256) k_filter_mark(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w, unsigned* masks,
                                                      unsigned n, int qslot) {
@@ -1129,6 +1230,8 @@ __global__ void __launch_bounds__(256) k_filter_pack(const __grid_constant__ Wav
         __syncthreads();   // s_cnt / s_base are reused by the next round
     }
 }
+
+#endif   // RT_OCT_SORT
 
 // Builds the stage list for a scene (host) and runs one tile through it.
 struct Stage { bool is_walk; StageOp op; int set; bool any; int qslot; };
@@ -1236,10 +1339,10 @@ int ensureWaveBuffers(rt_render* r) {
     const size_t nl = r->scene->lights.size() ? r->scene->lights.size() : 1;
     A((void**)&r->w_sh, sizeof(float4) * 2 * n * nl);      // one shadow ray per light and slot
     A((void**)&r->w_queue, sizeof(unsigned) * n * nl);     // any-hit walks queue (light, slot) entries
-    A((void**)&r->w_qctr, sizeof(unsigned) * 4 * kMaxStages);   // {count, head} per walk stage: [0, 2K) as pushed, [2K, 4K) filtered
+    A((void**)&r->w_qctr, sizeof(unsigned) * 1028 * kMaxStages);  // {count, head} per walk stage: [0, 2K) as pushed, [2K, 4K) filtered; [4K, 1028K) direction-class totals / cursors of the filter
     if (skipEmptyWalks()) {
         A((void**)&r->w_queue_f, sizeof(unsigned) * n * nl);              // what the queue filter leaves for the walker
-        A((void**)&r->w_masks, sizeof(unsigned) * ((n * nl + 31) / 32 + 8));   // its keep decisions, one bit per entry
+        A((void**)&r->w_masks, RT_OCT_SORT ? 2 * (n * nl + 64) : sizeof(unsigned) * ((n * nl + 31) / 32 + 8));   // its keep decisions, one bit (one code byte) per entry
     }
     return rc;
 }
@@ -1291,7 +1394,7 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
     WaveState wf = w;   // the filtered queue (k_filter) the walkers read when the empty-walk proof is on
     wf.queue = r->w_queue_f;
     wf.qctr = r->w_qctr + 2 * kMaxStages;
-    RT_CUDA(ctx, cudaMemsetAsync(r->w_qctr, 0, sizeof(unsigned) * 4 * kMaxStages, ctx->stream));
+    RT_CUDA(ctx, cudaMemsetAsync(r->w_qctr, 0, sizeof(unsigned) * 1028 * kMaxStages, ctx->stream));
     const unsigned n = a.n_local;
     const WaveState& w0 = w;
     for (const Stage& s : stages) {

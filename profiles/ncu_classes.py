@@ -39,7 +39,7 @@ def source_sha(root=ROOT):
 
 def classify(kernel):
     k = re.sub(r"<unnamed>::|\(anonymous namespace\)::", "", kernel)
-    m = re.search(r"k_walk_pairs<\(?(?:int\))?(\d),\s*\(?(?:bool\))?(\d|true|false)>", k)
+    m = re.search(r"k_walk_pairs<\(?(?:int\))?(\d),\s*\(?(?:bool\))?(\d|true|false)\s*[,>]", k)
     if m:
         prim = "sphere" if m.group(1) == "0" else "triangle"
         anyh = m.group(2) in ("1", "true")
