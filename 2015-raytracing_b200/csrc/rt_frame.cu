@@ -456,7 +456,7 @@ int rt_render_create(rt_ctx* ctx, rt_scene* scene, const rt_render_opts* opts, r
     // slots with two lights): the persistent queue walkers need a DEEP queue -- with 4 Mi-slot tiles a walk launch got
     // ~0.5 M rays for 151 k lanes and spent a quarter of its time in the drain tail
     const size_t nlq = scene->lights.size() ? scene->lights.size() : 1;
-    const size_t slot_bytes = 80 + 40 * nlq;   // + a second (filtered) queue entry per light
+    const size_t slot_bytes = 80 + 44 * nlq;   // + a second (filtered) queue entry and the filter's codes (<= 4 B) per light
     size_t want = r->o.tile_slots ? r->o.tile_slots : (size_t)(ctx->prop.totalGlobalMem / 4 / slot_bytes);
     if (want < ((size_t)1 << 22)) want = (size_t)1 << 22;
     if (want * nlq > 0xFFFFFFFFull) want = 0xFFFFFFFFull / nlq;   // queue entries are light * tile_slots + slot in 32 bits

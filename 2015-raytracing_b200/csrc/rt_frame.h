@@ -72,7 +72,7 @@ struct rt_render {
     unsigned* w_queue = nullptr;     // [n] slot ids of the current heavy-set walk
     unsigned* w_qctr = nullptr;      // [4*kMaxStages]: per walk stage {count, head}, as pushed and as filtered
     unsigned* w_queue_f = nullptr;   // [n * lights] the queue after the filter (empty-walk proof)
-    unsigned* w_masks = nullptr;     // [n * lights / 32] the filter's keep bits
+    unsigned* w_masks = nullptr;     // [n * lights] the filter's decisions (direction-class code per queue entry)
     // stats
     unsigned long long* d_counters = nullptr;   // [0] closest rays, [1] any rays
     unsigned long long* d_profile = nullptr;    // [RT_MAX_SETS][16] work counters per geometry set (rt_render_read_profile*)

@@ -33,6 +33,7 @@ struct SetDev {
     int far_ok;                // 1-cell sets: the cell's exit planes are bit for bit the box's far planes (see farPlanesShared)
     const unsigned char* macro_dist;   // heavy sets: chessboard distance of every cell of the distance field to the nearest occupied one (or null)
     float dist_inv[3];         // world -> field-index scale per axis
+    float org_unit[3];         // world -> unit cube of the set's box (the queue partition's origin blocks)
     unsigned dist_shift, dist_n;       // field cells are (2^dist_shift)^3 grid cells, dist_n per axis
     unsigned n_refs;
     int wall_ok;               // 1-cell triangle sets made of axis-aligned planar triangles ("walls"): see shadowClearsWalls
@@ -375,6 +376,7 @@ int buildSceneDev(rt_render* r, SceneDev& sc) {
         d.far_ok = (RT_FAR_SHARE && in.grid.n_slabs == 1 && farPlanesShared(in.bound)) ? 1 : 0;
         d.macro_dist = skipEmptyWalks() ? in.macro_dist : nullptr;
         for (int a = 0; a < 3; a++) d.dist_inv[a] = in.dist_inv[a];
+        for (int a = 0; a < 3; a++) d.org_unit[a] = in.dist_n ? in.dist_inv[a] / (float)in.dist_n : 0.f;
         d.dist_shift = in.dist_shift;
         d.dist_n = in.dist_n;
         d.n_refs = in.grid.n_refs;
@@ -514,7 +516,10 @@ template <class T> RT_DEV void stS(T* p, T v) {
 // warp there pays its slowest lane's march for 4 useful lanes (measured: stage 606 -> 724 ms, more than the walkers
 // gained) -- but in k_filter_mark, a pass over the compact queue between stage and walk where every lane has a ray to prove.
 // ---------------------------------------------------------------------------------------
-constexpr int kMaxMarch = 32;
+#ifndef RT_MAX_MARCH
+#define RT_MAX_MARCH 32
+#endif
+constexpr int kMaxMarch = RT_MAX_MARCH;   // undecided after that many steps = kept
 RT_DEV bool walkProvablyEmpty(f3 o, f3 d, float tmin, float tmax, const SetDev& s) {
     const unsigned char* dist = s.macro_dist;
     if (!dist) return false;
@@ -553,11 +558,14 @@ RT_DEV void pushTask(bool want, unsigned id, unsigned* queue, unsigned* count) {
 #ifndef RT_STAGE_MINB
 #define RT_STAGE_MINB 5
 #endif
+#ifndef RT_STAGE_MINB_BOUNCE   // the shade + bounce + closest-hit stage spills 186 B at 48 registers (5 blocks); at 64 (4 blocks):
+#define RT_STAGE_MINB_BOUNCE 4  // stage class 500.5 -> 491.7 ms.  4 blocks for every stage shape: 497; 3 blocks: 546
+#endif
 // GEN / LR / SHADE / SHADOW / KIND mirror StageOp's gen, light_render, shade, shadow and kind; they are template
 // parameters so that each of the few stage shapes a pass is made of gets its own register allocation (the
 // all-in-one kernel needed 80 registers or spilled ~400 B at 64).  The set ranges stay run-time values.
 template <int GEN, bool LR, bool SHADE, bool SHADOW, int KIND>
-__global__ void __launch_bounds__(256, RT_STAGE_MINB) k_stage(const __grid_constant__ SceneDev sc, const __grid_constant__ PathArgs a,
+__global__ void __launch_bounds__(256, (GEN == 2 && SHADE) ? RT_STAGE_MINB_BOUNCE : RT_STAGE_MINB) k_stage(const __grid_constant__ SceneDev sc, const __grid_constant__ PathArgs a,
                                                const __grid_constant__ WaveState w, const __grid_constant__ StageOp op) {
     const unsigned id = blockIdx.x * blockDim.x + threadIdx.x;
     const bool inb = id < a.n_local;
@@ -1082,20 +1090,33 @@ __global__ void __launch_bounds__(kWalkWarps * 32, kWalkMinBlocks) k_walk_pairs(
 // nanosecond: with one atomic per warp the first version spent 3.7 ms per launch on 3.3 M of them, three times its own work;
 // with the march inside the synchronised rounds it still took 2.7 ms).
 constexpr int kFilterBlocks = 8;   // per SM
+// RT_OCT_SORT (default on): the survivors leave the filter PARTITIONED, so that the 32 rays a walker warp pops together start in the
+// same part of the grid and step the same way through it -- a queue in slot order is coherent for primary rays only; bounce rays
+// of neighbouring slots leave in random hemisphere directions, and from the second bounce on they also start anywhere.  The order
+// of a queue never changes a result (every ray is independent and writes its own slot), so this is a pure scheduling choice.
+//   major key: DIRECTION CLASS -- the cube-map cell of the direction: face of the dominant component (6) x 4 x 4 = 96 classes;
+//   minor key (RT_ORG_SORT = G): the G^3 BLOCK OF THE SET'S BOX THE RAY ENTERS IN, Morton order.
+// mark writes both codes per entry and the class totals; two scatter passes follow, origin block first (pushed queue -> filtered
+// queue, the direction code travels along), direction class second (back into the pushed queue's buffer, which the walker then
+// reads).  The second pass is stable round-wise only (rounds of 4096 reach a class's cursor in arrival order): a class receives
+// ~43 consecutive entries of one origin block at a time, more than a warp pops.
+// Measured on B200, full config, same box each line (Mrays/s; any-hit / closest walks, stage + filter class, ms per step):
+//   no partition 7 814 (460 / 253); octant (8 classes) 7 977; octant x dominant axis (24) 8 004-8 048;
+//   cube map 4 x 4 (96) 8 033-8 070 (425 / 245); cube map 8 x 8 (384) 8 042 (419 / 246, stage + 4);
+//   + origin blocks, on top of cube map 4 x 4 = 8 100 (426 / 246, 500): 4^3 8 104 (409 / 236, 527); 8^3 8 169 (403 / 232, 528);
+//   16^3 with rounds of 4096 in the second pass 8 165 -> with a multiplication instead of three divisions in the block key
+//   8 324 together with RT_STAGE_MINB_BOUNCE = 4 (395 / 227, 519); per launch: mark 3.5 / 1.9 ms (any / closest; 2.7 / 1.5 without
+//   the origin key), origin pass 0.79 ms, direction pass 0.21 ms.
+//   Counting the classes with one shared-memory atomic per class present in the warp (match.any) instead of one per entry: slower
+//   (stage class 500 -> 508 ms).
 #ifndef RT_OCT_SORT
-#define RT_OCT_SORT 0
+#define RT_OCT_SORT 1
 #endif
 #if RT_OCT_SORT
-// The survivors leave the filter partitioned by the direction class of their ray -- octant (RT_OCT_SORT = 1), or octant and
-// dominant axis (= 2) -- with slot order kept inside a class up to rounds of 1024, so that the 32 rays of a walker warp step the
-// same way through neighbouring cells.  mark writes a code byte per entry (0 = dropped, 1 + class) and the class totals; pack
-// scatters into the classes' segments.
-constexpr int kDirGrid = RT_OCT_SORT >= 4 ? 8 : 4;   // cube-map cells per face and axis
-constexpr int kDirBins = RT_OCT_SORT >= 4 ? 512 : (RT_OCT_SORT == 3 ? 128 : 32);
-typedef unsigned short DirCode;
+constexpr int kDirGrid = 4;   // cube-map cells per face and axis
+constexpr int kDirBins = 128;   // >= 6 * kDirGrid^2
+typedef unsigned char DirCode;
 RT_DEV unsigned dirClass(f3 d) {
-#if RT_OCT_SORT >= 3
-    // cube-map cells: the face of the dominant component (6) x a 4 x 4 (RT_OCT_SORT = 3) grid of the other two, relative to it
     const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
     float m, u, v;
     unsigned face;
@@ -1106,23 +1127,42 @@ RT_DEV unsigned dirClass(f3 d) {
     const float r = m > 0.f ? h / m : 0.f;   // (-1, 1) -> (0, kDirGrid)
     const int iu = min(max((int)(u * r + h), 0), kDirGrid - 1), iv = min(max((int)(v * r + h), 0), kDirGrid - 1);
     return face * (unsigned)(kDirGrid * kDirGrid) + (unsigned)(iu * kDirGrid + iv);
-#endif
-    const unsigned oct = (d.x < 0.f ? 1u : 0u) | (d.y < 0.f ? 2u : 0u) | (d.z < 0.f ? 4u : 0u);
-#if RT_OCT_SORT == 2
-    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    const unsigned dom = (ax >= ay && ax >= az) ? 0u : (ay >= az ? 1u : 2u);
-    return oct * 3u + dom;
-#else
-    return oct;
-#endif
 }
+#ifndef RT_ORG_SORT
+#define RT_ORG_SORT 16   // 0 = direction classes only; <= 16 (Morton key of 4 bits per axis)
+#endif
+#ifndef RT_PACK2_PER   // round size of the second pass / 256: a class gets ROUND / 96 consecutive entries of one origin block
+#define RT_PACK2_PER 16
+#endif
+constexpr int kOrgGrid = RT_ORG_SORT;
+constexpr int kOrgBins = RT_ORG_SORT ? RT_ORG_SORT * RT_ORG_SORT * RT_ORG_SORT : 1;
+#if RT_ORG_SORT > 4
+typedef unsigned short OrgCode;
+#else
+typedef unsigned char OrgCode;
+#endif
+constexpr int kSortCtrs = 2 * kDirBins + 2 * kOrgBins;   // per walk stage: class totals + cursors of either pass
+RT_DEV unsigned spread3(unsigned v) {   // 4 bits -> every third bit
+    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+}
+RT_DEV unsigned orgClass(f3 o, f3 d, float tmin, const SetDev& set) {
+    // the block of the entry point in a kOrgGrid^3 partition of the set's box; org_unit = 1 / extent (a binning key only)
+    const AABB& b = set.g.bound;
+    const f3 p = o + tmin * d;
+    const int ix = min(max((int)((p.x - b.pmin.x) * (set.org_unit[0] * (float)kOrgGrid)), 0), kOrgGrid - 1);
+    const int iy = min(max((int)((p.y - b.pmin.y) * (set.org_unit[1] * (float)kOrgGrid)), 0), kOrgGrid - 1);
+    const int iz = min(max((int)((p.z - b.pmin.z) * (set.org_unit[2] * (float)kOrgGrid)), 0), kOrgGrid - 1);
+    return spread3((unsigned)ix) | (spread3((unsigned)iy) << 1) | (spread3((unsigned)iz) << 2);
+}
+// codes: [0, cap) DirCode in queue order; with RT_ORG_SORT also [cap, 2 cap) DirCode in origin order and, behind them, OrgCode[cap]
 template <bool ANY>
 __global__ void __launch_bounds__(256) k_filter_mark(const __grid_constant__ SetDev set, const __grid_constant__ WaveState w, unsigned* masks,
-                                                     unsigned n, int qslot) {
-    __shared__ unsigned s_hist[kDirBins];
-    for (int k = threadIdx.x; k < kDirBins; k += 256) s_hist[k] = 0;
+                                                     unsigned n, size_t cap, int qslot) {
+    __shared__ unsigned s_hist[kDirBins + kOrgBins];
+    for (int k = threadIdx.x; k < kDirBins + kOrgBins; k += 256) s_hist[k] = 0;
     __syncthreads();
     DirCode* codes = (DirCode*)masks;
+    OrgCode* ocodes = (OrgCode*)(codes + 2 * cap);
     const unsigned count = w.qctr[2 * qslot];
     const unsigned lane = threadIdx.x & 31;
     const unsigned words = (count + 31u) / 32u;
@@ -1138,46 +1178,65 @@ __global__ void __launch_bounds__(256) k_filter_mark(const __grid_constant__ Set
             const AabbHit bi = interAABB(o, d, set.g.bound);
             const bool keep = !(bi.tmin * 0.9999f > r1.w) && !walkProvablyEmpty(o, d, bi.tmin, bi.tmax, set);
             const unsigned cls = dirClass(d);
-            codes[idx] = keep ? (DirCode)(1u + cls) : (DirCode)0;
+            // (one shared-memory atomic per entry: aggregating per warp with match.any was measured slower, stage class 500 -> 508 ms)
+            if (RT_ORG_SORT) {
+                const unsigned oc = orgClass(o, d, bi.tmin, set);
+                codes[idx] = (DirCode)(1u + cls);
+                ocodes[idx] = keep ? (OrgCode)(1u + oc) : (OrgCode)0;
+                if (keep) atomicAdd(&s_hist[kDirBins + oc], 1u);
+            } else {
+                codes[idx] = keep ? (DirCode)(1u + cls) : (DirCode)0;
+            }
             if (keep) atomicAdd(&s_hist[cls], 1u);
         }
     }
     __syncthreads();
+    unsigned* ctr = w.qctr + 4 * kMaxStages + kSortCtrs * qslot;
     for (int k = threadIdx.x; k < kDirBins; k += 256)
-        if (s_hist[k]) atomicAdd(w.qctr + 4 * kMaxStages + 2 * kDirBins * qslot + k, s_hist[k]);
+        if (s_hist[k]) atomicAdd(ctr + k, s_hist[k]);
+    if (RT_ORG_SORT)
+        for (int k = threadIdx.x; k < kOrgBins; k += 256)
+            if (s_hist[kDirBins + k]) atomicAdd(ctr + 2 * kDirBins + k, s_hist[kDirBins + k]);
 }
 
-__global__ void __launch_bounds__(256) k_filter_pack(const __grid_constant__ WaveState w, const __grid_constant__ WaveState wf,
-                                                     const unsigned* masks, int qslot) {
-    __shared__ unsigned s_loc[kDirBins], s_glob[kDirBins], s_base[kDirBins];
-    const DirCode* codes = (const DirCode*)masks;
-    const unsigned count = w.qctr[2 * qslot];
-    const unsigned* tot = w.qctr + 4 * kMaxStages + 2 * kDirBins * qslot;
-    unsigned* pos = w.qctr + 4 * kMaxStages + 2 * kDirBins * qslot + kDirBins;
+// One scatter pass: the entries of qin with a non-zero code go to their class's segment of qout (classes in index order);
+// ctr = BINS class totals followed by BINS cursors.  CARRY moves a byte per entry along (the other pass's code).
+template <typename CodeT, int BINS, bool CARRY, int PER>   // PER = entries per thread and round
+__global__ void __launch_bounds__(256) k_filter_pack(const unsigned* __restrict__ qin, unsigned* __restrict__ qout, const CodeT* __restrict__ codes,
+                                                     const DirCode* __restrict__ carry_in, DirCode* __restrict__ carry_out,
+                                                     const unsigned* __restrict__ count_ptr, unsigned* __restrict__ ctr, unsigned* out_count) {
+    constexpr unsigned ROUND = 256u * PER;
+    __shared__ unsigned s_loc[BINS], s_glob[BINS], s_base[BINS];
+    const unsigned count = *count_ptr;
+    const unsigned* tot = ctr;
+    unsigned* pos = ctr + BINS;
     if (threadIdx.x == 0) {
         unsigned acc = 0;
-        for (int k = 0; k < kDirBins; k++) { s_base[k] = acc; acc += tot[k]; }
-        if (blockIdx.x == 0) wf.qctr[2 * qslot] = acc;   // what the walker will find in the filtered queue
+        for (int k = 0; k < BINS; k++) { s_base[k] = acc; acc += tot[k]; }
+        if (blockIdx.x == 0 && out_count) *out_count = acc;   // what the walker will find in the filtered queue
     }
-    const unsigned rounds = (count + 1023u) / 1024u;
+    const unsigned rounds = (count + ROUND - 1u) / ROUND;
     for (unsigned round = blockIdx.x; round < rounds; round += gridDim.x) {
-        for (int k = threadIdx.x; k < kDirBins; k += 256) s_loc[k] = 0;
+        for (int k = threadIdx.x; k < BINS; k += 256) s_loc[k] = 0;
         __syncthreads();
-        unsigned code[4], rank[4];
+        unsigned code[PER], rank[PER];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const unsigned idx = round * 1024u + k * 256u + threadIdx.x;
+        for (int k = 0; k < PER; k++) {
+            const unsigned idx = round * ROUND + k * 256u + threadIdx.x;
             code[k] = idx < count ? codes[idx] : 0u;
             rank[k] = code[k] ? atomicAdd(&s_loc[code[k] - 1u], 1u) : 0u;
         }
         __syncthreads();
-        for (int k = threadIdx.x; k < kDirBins; k += 256) s_glob[k] = s_loc[k] ? atomicAdd(pos + k, s_loc[k]) : 0u;
+        for (int k = threadIdx.x; k < BINS; k += 256) s_glob[k] = s_loc[k] ? atomicAdd(pos + k, s_loc[k]) : 0u;
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < PER; k++)
             if (code[k]) {
                 const unsigned o = code[k] - 1u;
-                stS(wf.queue + s_base[o] + s_glob[o] + rank[k], ldS(w.queue + round * 1024u + k * 256u + threadIdx.x));
+                const unsigned idx = round * ROUND + k * 256u + threadIdx.x;
+                const unsigned dst = s_base[o] + s_glob[o] + rank[k];
+                stS(qout + dst, ldS(qin + idx));
+                if (CARRY) carry_out[dst] = carry_in[idx];
             }
         __syncthreads();
     }
@@ -1232,6 +1291,13 @@ __global__ void __launch_bounds__(256) k_filter_pack(const __grid_constant__ Wav
 }
 
 #endif   // RT_OCT_SORT
+#if RT_OCT_SORT
+constexpr size_t kQctrWords = (size_t)(4 + kSortCtrs) * kMaxStages;
+constexpr size_t kCodeBytes = RT_ORG_SORT ? 2 * sizeof(DirCode) + sizeof(OrgCode) : sizeof(DirCode);
+#else
+constexpr size_t kQctrWords = (size_t)4 * kMaxStages;
+constexpr size_t kCodeBytes = 0;
+#endif
 
 // Builds the stage list for a scene (host) and runs one tile through it.
 struct Stage { bool is_walk; StageOp op; int set; bool any; int qslot; };
@@ -1339,10 +1405,10 @@ int ensureWaveBuffers(rt_render* r) {
     const size_t nl = r->scene->lights.size() ? r->scene->lights.size() : 1;
     A((void**)&r->w_sh, sizeof(float4) * 2 * n * nl);      // one shadow ray per light and slot
     A((void**)&r->w_queue, sizeof(unsigned) * n * nl);     // any-hit walks queue (light, slot) entries
-    A((void**)&r->w_qctr, sizeof(unsigned) * 1028 * kMaxStages);  // {count, head} per walk stage: [0, 2K) as pushed, [2K, 4K) filtered; [4K, 1028K) direction-class totals / cursors of the filter
+    A((void**)&r->w_qctr, sizeof(unsigned) * kQctrWords);  // {count, head} per walk stage: [0, 2K) as pushed, [2K, 4K) filtered; behind them the class totals / cursors of the filter's partition
     if (skipEmptyWalks()) {
         A((void**)&r->w_queue_f, sizeof(unsigned) * n * nl);              // what the queue filter leaves for the walker
-        A((void**)&r->w_masks, RT_OCT_SORT ? 2 * (n * nl + 64) : sizeof(unsigned) * ((n * nl + 31) / 32 + 8));   // its keep decisions, one bit (one code byte) per entry
+        A((void**)&r->w_masks, kCodeBytes ? kCodeBytes * (n * nl + 64) : sizeof(unsigned) * ((n * nl + 31) / 32 + 8));   // its decisions: a class code (or one keep bit) per entry
     }
     return rc;
 }
@@ -1394,7 +1460,11 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
     WaveState wf = w;   // the filtered queue (k_filter) the walkers read when the empty-walk proof is on
     wf.queue = r->w_queue_f;
     wf.qctr = r->w_qctr + 2 * kMaxStages;
-    RT_CUDA(ctx, cudaMemsetAsync(r->w_qctr, 0, sizeof(unsigned) * 1028 * kMaxStages, ctx->stream));
+    WaveState wg = wf;   // what the walkers read: with the two-pass partition the second pass lands in the pushed queue's buffer
+#if RT_OCT_SORT
+    if (RT_ORG_SORT) wg.queue = r->w_queue;
+#endif
+    RT_CUDA(ctx, cudaMemsetAsync(r->w_qctr, 0, sizeof(unsigned) * kQctrWords, ctx->stream));
     const unsigned n = a.n_local;
     const WaveState& w0 = w;
     for (const Stage& s : stages) {
@@ -1413,13 +1483,32 @@ int waveTile(rt_render* r, const SceneDev& sc, const PathArgs& a) {
             if (filtered) {
                 RT_TRY_W(rt_time_mark(r, 0));   // charged to the stage class: it is queue preparation
                 const int fb = ctx->prop.multiProcessorCount * kFilterBlocks;
+#if RT_OCT_SORT
+                const size_t cap = (size_t)n * (r->scene->lights.size() ? r->scene->lights.size() : 1) + 64;
+                DirCode* dc = (DirCode*)r->w_masks;
+                unsigned* ctr = r->w_qctr + 4 * kMaxStages + kSortCtrs * s.qslot;
+                if (s.any) k_filter_mark<true><<<fb, 256, 0, ctx->stream>>>(set, w, r->w_masks, n, cap, s.qslot);
+                else k_filter_mark<false><<<fb, 256, 0, ctx->stream>>>(set, w, r->w_masks, n, cap, s.qslot);
+                RT_LAUNCH_CHECK(ctx, "wave_filter_mark");
+                if (RT_ORG_SORT) {   // origin block first (into the filtered queue), direction class second (back into the pushed queue)
+                    k_filter_pack<OrgCode, kOrgBins, true, (kOrgBins > 512 ? 16 : 4)><<<fb, 256, 0, ctx->stream>>>(w.queue, wf.queue, (const OrgCode*)(dc + 2 * cap), dc, dc + cap,
+                                                                                       w.qctr + 2 * s.qslot, ctr + 2 * kDirBins, wf.qctr + 2 * s.qslot);
+                    RT_LAUNCH_CHECK(ctx, "wave_filter_pack_origin");
+                    k_filter_pack<DirCode, kDirBins, false, RT_PACK2_PER><<<fb, 256, 0, ctx->stream>>>(wf.queue, w.queue, dc + cap, nullptr, nullptr,
+                                                                                        wf.qctr + 2 * s.qslot, ctr, nullptr);
+                } else {
+                    k_filter_pack<DirCode, kDirBins, false, 4><<<fb, 256, 0, ctx->stream>>>(w.queue, wf.queue, dc, nullptr, nullptr, w.qctr + 2 * s.qslot, ctr,
+                                                                                        wf.qctr + 2 * s.qslot);
+                }
+#else
                 if (s.any) k_filter_mark<true><<<fb, 256, 0, ctx->stream>>>(set, w, r->w_masks, n, s.qslot);
                 else k_filter_mark<false><<<fb, 256, 0, ctx->stream>>>(set, w, r->w_masks, n, s.qslot);
                 RT_LAUNCH_CHECK(ctx, "wave_filter_mark");
                 k_filter_pack<<<fb, 256, 0, ctx->stream>>>(w, wf, r->w_masks, s.qslot);
+#endif
                 RT_LAUNCH_CHECK(ctx, "wave_filter_pack");
             }
-            const WaveState& w = filtered ? wf : *&w0;
+            const WaveState& w = filtered ? wg : *&w0;
             RT_TRY_W(rt_time_mark(r, (set.kind == PRIM_SPHERE ? 1 : 3) + (s.any ? 1 : 0)));
             if (set.kind == PRIM_SPHERE) {
                 if (s.any) k_walk_pairs<PRIM_SPHERE, true><<<walk_blocks, kWalkWarps * 32, 0, ctx->stream>>>(set, w, n, s.qslot);
