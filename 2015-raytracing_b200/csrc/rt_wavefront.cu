@@ -517,7 +517,7 @@ template <class T> RT_DEV void stS(T* p, T v) {
 // gained) -- but in k_filter_mark, a pass over the compact queue between stage and walk where every lane has a ray to prove.
 // ---------------------------------------------------------------------------------------
 #ifndef RT_MAX_MARCH
-#define RT_MAX_MARCH 32
+#define RT_MAX_MARCH 16
 #endif
 constexpr int kMaxMarch = RT_MAX_MARCH;   // undecided after that many steps = kept
 RT_DEV bool walkProvablyEmpty(f3 o, f3 d, float tmin, float tmax, const SetDev& s) {
@@ -753,7 +753,7 @@ __global__ void __launch_bounds__(256, (GEN == 2 && SHADE) ? RT_STAGE_MINB_BOUNC
 // least kRefill lanes of the warp are idle (or none has work) the warp pops that many slot ids with ONE
 // atomicAdd and the idle lanes set up their DDA.
 #ifndef RT_REFILL
-#define RT_REFILL 8
+#define RT_REFILL 24
 #endif
 constexpr int kRefill = RT_REFILL;
 #ifndef RT_STEP_BURST
@@ -796,12 +796,14 @@ constexpr int kCandCap = 64;
 //             32 survivors have been collected.                         L1: 6119, L2: 6115 Mrays/s  -> on (L1)
 //   RT_PF_NG: when a lane enters a non-empty cell, request the lines of that cell's face vectors right away.
 //             L1: 5895, L2: 5897 Mrays/s (the extra instructions in the step loop cost more than the hint saves) -> off
+//   On the partitioned queue (round 2: the rays of a warp visit neighbouring cells, the lines are in L1 anyway): RT_PF_PE off 8 630 vs
+//   on 8 590 Mrays/s (any-hit walks 372 vs 377 ms); RT_PF_NG on 8 307 -> both off.
 // 0 = off, 1 = into L1, 2 = into L2.
 #ifndef RT_PF_NG
 #define RT_PF_NG 0
 #endif
 #ifndef RT_PF_PE
-#define RT_PF_PE 1
+#define RT_PF_PE 0
 #endif
 template <int LEVEL>
 RT_DEV void prefetchLine(const void* p) {
