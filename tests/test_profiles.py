@@ -51,3 +51,27 @@ def test_bench_accepts_the_committed_profile():
     args.spp = 4
     best, note = bench.load_ncu_classes(args, 1)
     assert best is None and "non-default" in note
+
+
+def _fmt(v):
+    s = "%d" % round(v)
+    return s[:-3] + " " + s[-3:] if len(s) > 3 else s   # "8 705" as the documents write it
+
+
+def test_documents_quote_the_committed_bench_lines():
+    """README.md and DESIGN.md quote the headline numbers; they must be the ones of the newest committed bench lines."""
+    pdir = os.path.join(ROOT, "profiles")
+    sha_of = {fn: d.get("source_sha") for fn, d in _profiles()}
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import ncu_classes
+    tag = [fn.split("_")[0] for fn, sha in sha_of.items() if sha == ncu_classes.source_sha(ROOT)][-1]
+    line = json.load(open(os.path.join(pdir, tag + "_bench.json")))
+    assert line["n_gpus"] == 1 and line["roofline"]["ncu_profile"] == tag + "_ncu_classes.json"
+    want = [_fmt(line["value"]), _fmt(line["e2e"]["value"])]
+    n8 = os.path.join(pdir, tag + "_bench_n8.json")
+    if os.path.exists(n8):
+        want.append(_fmt(json.load(open(n8))["value"]))
+    for doc in ("README.md", "DESIGN.md"):
+        text = open(os.path.join(ROOT, doc), encoding="utf-8").read().replace(" ", " ").replace(" ", " ")
+        for w in want:
+            assert w in text, "%s does not quote %s (profiles/%s_bench*.json)" % (doc, w, tag)
