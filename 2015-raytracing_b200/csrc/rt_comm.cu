@@ -39,7 +39,8 @@ NcclApi& nccl() {
         if (api.handle) break;
     }
     if (!api.handle) {
-        api.error = std::string("NCCL not found (libnccl.so.2): ") + (dlerror() ? dlerror() : "dlopen failed");
+        const char* why = dlerror();   // one call: dlerror() clears the message it returns
+        api.error = std::string("NCCL not found (libnccl.so.2): ") + (why ? why : "dlopen failed");
         return api;
     }
     auto sym = [&](const char* s) -> void* {

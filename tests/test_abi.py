@@ -72,6 +72,20 @@ def test_null_arguments_are_rejected(rt):
     assert dll.rt_last_error_string(None) == b"null context"
 
 
+def test_comm_id_needs_no_gpu(rt):
+    """rt_comm_unique_id binds NCCL at run time (dlopen) and needs neither a context nor a device: it either hands out a 128-byte id or
+    fails with a status -- never a crash -- and rejects a null pointer before touching NCCL."""
+    import ctypes
+    f = rt.lib.dll.rt_comm_unique_id
+    f.restype = ctypes.c_int
+    assert f(None) == -1   # RT_ERR_INVALID
+    buf = (ctypes.c_ubyte * 128)()
+    rc = f(buf)
+    assert rc <= 0
+    if rc == 0:
+        assert any(bytes(buf))
+
+
 def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure: nothing under the package may import or load it."""
     pkg = os.path.join(ROOT, "2015-raytracing_b200")
