@@ -57,6 +57,10 @@ class Comm:
         import ctypes as C
 
         from . import lib as L
+        try:   # PyTorch's bundled libnccl.so.2 must be the one the process binds: once the system's older one is loaded under
+            import torch  # noqa: F401  -- the same soname, a later `import torch` fails on the symbols it lacks
+        except ImportError:
+            pass
         self.ctx, self.rank, self.world = ctx, int(rank), int(world)
         ident = (C.c_ubyte * 128)()
         if rank == 0:
